@@ -1,0 +1,261 @@
+// Window extraction: sliding-window box -> fixed-size patch (sm_100a).
+//
+// Replaces load_network_subimages (reference face_analysis.py:775-800) ->
+// cuicuilco extract_subimages_rotate + images_asarray -> Pillow Image.transform(size, EXTENT, box,
+// NEAREST | BILINEAR), one Python iteration and one C call per window.
+//
+// Two kernels:
+//  1. crop_index_kernel: per window and axis, the 64-entry source-index table of Pillow's NEAREST
+//     resampler, reproduced bit-exactly: a = (hi - lo) / n in double, xo = lo + a * 0.5, then n
+//     *sequential* double additions (ImagingScaleAffine accumulates; the multiply form differs in the
+//     last bit on some boxes -- SURVEY.md Appendix B.3).  -1 marks out-of-image.
+//  2. crop_gather_kernel: CTA = (tile of 128 windows, group of output rows).  Lanes run along the
+//     output columns of one window, so a warp's 32 byte-gathers fall into 1-4 cache lines of one
+//     image row (the image is L2-resident); patches are transposed through shared memory and
+//     written window-minor ("TILED") so that the flow kernels read them with 512-byte warp accesses,
+//     or written row-major for the drop-in host API.
+// Rotated windows (angle != 0) and BILINEAR take the generic per-pixel affine path in the same kernel.
+#include "common.cuh"
+
+namespace hgsfa {
+
+constexpr int TILE_W = HGSFA_TILE;
+
+__global__ void crop_index_kernel(const double* __restrict__ boxes, int64_t n, int ow, int oh, int W, int H,
+                                  int* __restrict__ xtab, int* __restrict__ ytab) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= 2 * n) return;
+  const int64_t w = t >> 1;
+  const int axis = int(t & 1);
+  const double lo = boxes[w * 4 + axis], hi = boxes[w * 4 + 2 + axis];
+  const int cnt = axis ? oh : ow;
+  const int size = axis ? H : W;
+  int* tab = (axis ? ytab + w * oh : xtab + w * ow);
+  const double a = __ddiv_rn(__dsub_rn(hi, lo), double(cnt));
+  double xo = __dadd_rn(lo, __dmul_rn(a, 0.5));
+  for (int c = 0; c < cnt; ++c) {
+    int idx = -1;
+    if (!(xo < 0.0)) {
+      // C (int) cast of a non-negative double; anything at or beyond `size` is out of the image
+      if (xo < double(size)) idx = int(xo);
+    }
+    tab[c] = idx;
+    xo = __dadd_rn(xo, a);
+  }
+}
+
+__device__ __forceinline__ double bilinear_at(const uint8_t* __restrict__ img, int W, int H, double xin, double yin,
+                                             bool* valid) {
+  // Pillow bilinear_filter8: reject outside [0, size); shift by -0.5; floor; lerp with clamped neighbours
+  if (!(xin >= 0.0 && xin < double(W) && yin >= 0.0 && yin < double(H))) { *valid = false; return 0.0; }
+  *valid = true;
+  const double xs = __dsub_rn(xin, 0.5), ys = __dsub_rn(yin, 0.5);
+  const double xf = floor(xs), yf = floor(ys);
+  const int x = int(xf), y = int(yf);
+  const double dx = __dsub_rn(xs, xf), dy = __dsub_rn(ys, yf);
+  const int x0 = min(max(x, 0), W - 1), x1 = min(max(x + 1, 0), W - 1);
+  const int y0 = min(max(y, 0), H - 1), y1 = min(max(y + 1, 0), H - 1);
+  const double p00 = img[size_t(y0) * W + x0], p01 = img[size_t(y0) * W + x1];
+  const double p10 = img[size_t(y1) * W + x0], p11 = img[size_t(y1) * W + x1];
+  const double v1 = __dadd_rn(p00, __dmul_rn(__dsub_rn(p01, p00), dx));
+  const double v2 = __dadd_rn(p10, __dmul_rn(__dsub_rn(p11, p10), dx));
+  return __dadd_rn(v1, __dmul_rn(__dsub_rn(v2, v1), dy));
+}
+
+// generic sample of output pixel (c, r) of window `box` rotated by delta_ang = -angle about its centre
+__device__ __forceinline__ uint8_t sample_generic(const uint8_t* __restrict__ img, int W, int H, const double* box,
+                                                  double cs, double sn, bool rotated, int ow, int oh, int c, int r,
+                                                  int filter) {
+  const double x0 = box[0], y0 = box[1], x1 = box[2], y1 = box[3];
+  const double ax = __ddiv_rn(__dsub_rn(x1, x0), double(ow)), ay = __ddiv_rn(__dsub_rn(y1, y0), double(oh));
+  double X, Y;
+  if (rotated) {
+    const double cx = __dmul_rn(__dadd_rn(x0, x1), 0.5), cy = __dmul_rn(__dadd_rn(y0, y1), 0.5);
+    const double u = __dsub_rn(__dadd_rn(__dmul_rn(ax, double(c) + 0.5), x0), cx);
+    const double v = __dsub_rn(__dadd_rn(__dmul_rn(ay, double(r) + 0.5), y0), cy);
+    X = __dadd_rn(cx, __dsub_rn(__dmul_rn(u, cs), __dmul_rn(v, sn)));
+    Y = __dadd_rn(cy, __dadd_rn(__dmul_rn(u, sn), __dmul_rn(v, cs)));
+  } else {
+    X = __dadd_rn(__dmul_rn(ax, double(c) + 0.5), x0);
+    Y = __dadd_rn(__dmul_rn(ay, double(r) + 0.5), y0);
+  }
+  if (filter == HGSFA_BILINEAR) {
+    bool valid;
+    const double v = bilinear_at(img, W, H, X, Y, &valid);
+    return valid ? uint8_t(v) : uint8_t(0);  // mode 'L': truncation
+  }
+  if (!(X >= 0.0 && Y >= 0.0)) return 0;
+  if (!(X < double(W) && Y < double(H))) return 0;
+  return img[size_t(int(Y)) * W + int(X)];
+}
+
+template <typename T>
+__device__ __forceinline__ T cvt_px(uint8_t v) { return T(v); }
+
+// grid (n_tiles, ceil(oh / ROWS)); 256 threads.  OUT_TILED: dst[tile][pixel][128]; else dst[window][pixel].
+template <typename OUT_T, bool OUT_TILED>
+__global__ void __launch_bounds__(256) crop_gather_kernel(const uint8_t* __restrict__ img, int H, int W,
+                                                          const double* __restrict__ boxes,
+                                                          const double* __restrict__ angles, int64_t n, int ow, int oh,
+                                                          int filter, const int* __restrict__ xtab,
+                                                          const int* __restrict__ ytab, OUT_T* __restrict__ dst,
+                                                          int rows_per_cta) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // staging of one output row for the whole tile: [ow][TILE_W + 4] bytes (padding breaks bank conflicts)
+  uint8_t* stage = smem_raw;
+  const int stage_ld = TILE_W + 4;
+  const int64_t tile = blockIdx.x;
+  const int r_begin = blockIdx.y * rows_per_cta;
+  const int r_end = min(oh, r_begin + rows_per_cta);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int npix = ow * oh;
+
+  for (int r = r_begin; r < r_end; ++r) {
+    // each warp extracts row r of windows warp, warp + 8, ...
+    for (int wl = warp; wl < TILE_W; wl += 8) {
+      const int64_t w = tile * TILE_W + wl;
+      const bool live = w < n;
+      double ang = 0.0;
+      if (live && angles) ang = angles[w];
+      const bool generic = live && (ang != 0.0 || filter != HGSFA_NEAREST);
+      double cs = 1.0, sn = 0.0;
+      double box[4] = {0, 0, 0, 0};
+      if (generic) {
+        box[0] = boxes[w * 4 + 0]; box[1] = boxes[w * 4 + 1]; box[2] = boxes[w * 4 + 2]; box[3] = boxes[w * 4 + 3];
+        if (ang != 0.0) {
+          // the reference extracts with delta_ang = -angle (face_analysis.py:781)
+          const double th = __ddiv_rn(__dmul_rn(-ang, 3.141592653589793), 180.0);
+          sincos(th, &sn, &cs);
+        }
+      }
+      const int y = (live && !generic) ? ytab[w * oh + r] : -1;
+      const uint8_t* row = img + size_t(max(y, 0)) * W;
+      for (int c = lane; c < ow; c += 32) {
+        uint8_t v = 0;
+        if (generic) {
+          v = sample_generic(img, W, H, box, cs, sn, ang != 0.0, ow, oh, c, r, filter);
+        } else if (y >= 0) {
+          const int x = xtab[w * ow + c];
+          if (x >= 0) v = __ldg(row + x);
+        }
+        if (OUT_TILED) {
+          stage[c * stage_ld + wl] = v;
+        } else if (live) {
+          dst[size_t(w) * npix + size_t(r) * ow + c] = cvt_px<OUT_T>(v);
+        }
+      }
+    }
+    if (OUT_TILED) {
+      __syncthreads();
+      // 128 consecutive windows of one pixel are contiguous in the tiled layout
+      for (int idx = tid; idx < ow * (TILE_W / 4); idx += 256) {
+        const int c = idx / (TILE_W / 4), q = idx % (TILE_W / 4);
+        const uchar4 v = *reinterpret_cast<const uchar4*>(stage + c * stage_ld + q * 4);
+        OUT_T* o = dst + (size_t(tile) * npix + size_t(r) * ow + c) * TILE_W + q * 4;
+        if (sizeof(OUT_T) == 1) {
+          *reinterpret_cast<uchar4*>(o) = v;
+        } else {
+          o[0] = cvt_px<OUT_T>(v.x); o[1] = cvt_px<OUT_T>(v.y); o[2] = cvt_px<OUT_T>(v.z); o[3] = cvt_px<OUT_T>(v.w);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct CropScratch {
+  DevBuf xtab, ytab;
+};
+
+// per-device scratch for the index tables (grow-only)
+static CropScratch& scratch_for(int device) {
+  static thread_local CropScratch s[16];
+  return s[device & 15];
+}
+
+}  // namespace hgsfa
+
+using namespace hgsfa;
+
+extern "C" int hgsfa_crop_extent_device(const uint8_t* d_img, int H, int W, const double* d_boxes,
+                                        const double* d_angles, int64_t n, int ow, int oh, int filter, void* d_out,
+                                        int out_dtype, int out_layout, void* stream) {
+  HG_CHECK(H > 0 && W > 0 && ow > 0 && oh > 0, "hgsfa_crop_extent: bad sizes H=%d W=%d ow=%d oh=%d", H, W, ow, oh);
+  HG_CHECK(ow <= 1024 && oh <= 1024, "hgsfa_crop_extent: patch size %dx%d too large", ow, oh);
+  HG_CHECK(filter == HGSFA_NEAREST || filter == HGSFA_BILINEAR,
+           "hgsfa_crop_extent: unsupported interpolation %d (NEAREST=0, BILINEAR=2)", filter);
+  HG_CHECK(n >= 0, "hgsfa_crop_extent: negative window count");
+  HG_CHECK(out_layout == HGSFA_ROWMAJOR || (out_layout == HGSFA_TILED && out_dtype != HGSFA_F64),
+           "hgsfa_crop_extent: tiled output must be u8 or f32");
+  if (n == 0) return 0;
+  HG_CHECK(d_img && d_boxes && d_out, "hgsfa_crop_extent: null buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int device = 0;
+  HG_CUDA(cudaGetDevice(&device));
+  CropScratch& sc = scratch_for(device);
+  if (sc.xtab.reserve(size_t(n) * ow * sizeof(int))) return 1;
+  if (sc.ytab.reserve(size_t(n) * oh * sizeof(int))) return 1;
+  int* xtab = static_cast<int*>(sc.xtab.p);
+  int* ytab = static_cast<int*>(sc.ytab.p);
+  crop_index_kernel<<<(unsigned)ceil_div(2 * n, 128), 128, 0, st>>>(d_boxes, n, ow, oh, W, H, xtab, ytab);
+  HG_CUDA(cudaGetLastError());
+
+  const int rows_per_cta = 8;
+  dim3 grid((unsigned)ceil_div(n, TILE_W), (unsigned)ceil_div(oh, rows_per_cta));
+  const size_t smem = size_t(ow) * (TILE_W + 4);
+#define HG_LAUNCH_CROP(T, TILED)                                                                                   \
+  crop_gather_kernel<T, TILED><<<grid, 256, (TILED) ? smem : 0, st>>>(d_img, H, W, d_boxes, d_angles, n, ow, oh, filter, \
+                                                                      xtab, ytab, static_cast<T*>(d_out), rows_per_cta)
+  if (out_layout == HGSFA_TILED) {
+    if (out_dtype == HGSFA_U8) HG_LAUNCH_CROP(uint8_t, true);
+    else HG_LAUNCH_CROP(float, true);
+  } else {
+    if (out_dtype == HGSFA_U8) HG_LAUNCH_CROP(uint8_t, false);
+    else if (out_dtype == HGSFA_F32) HG_LAUNCH_CROP(float, false);
+    else HG_LAUNCH_CROP(double, false);
+  }
+#undef HG_LAUNCH_CROP
+  HG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hgsfa_crop_extent(const uint8_t* img, int H, int W, const double* boxes, const double* angles,
+                                 int64_t n, int ow, int oh, int filter, void* out, int out_dtype, int device,
+                                 void* stream) {
+  HG_CHECK(n >= 0, "hgsfa_crop_extent: negative window count");
+  if (n == 0) return 0;
+  HG_CHECK(img && boxes && out, "hgsfa_crop_extent: null buffer");
+  HG_CHECK(H > 0 && W > 0 && ow > 0 && oh > 0, "hgsfa_crop_extent: bad sizes H=%d W=%d ow=%d oh=%d", H, W, ow, oh);
+  DeviceGuard guard(device);
+  HG_CHECK(guard.ok, "hgsfa_crop_extent: cannot select device %d", device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t out_bytes = size_t(n) * ow * oh * dtype_size(out_dtype);
+  uint8_t* d_img = nullptr;
+  double *d_boxes = nullptr, *d_angles = nullptr;
+  void* d_out = nullptr;
+  int rc = 1;
+  do {
+    if (cudaMalloc(&d_img, size_t(H) * W) != cudaSuccess || cudaMalloc(&d_boxes, size_t(n) * 4 * sizeof(double)) != cudaSuccess ||
+        (angles && cudaMalloc(&d_angles, size_t(n) * sizeof(double)) != cudaSuccess) ||
+        cudaMalloc(&d_out, out_bytes) != cudaSuccess) {
+      fail("hgsfa_crop_extent: device allocation failed (%zu output bytes)", out_bytes);
+      break;
+    }
+    if (cudaMemcpyAsync(d_img, img, size_t(H) * W, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(d_boxes, boxes, size_t(n) * 4 * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        (angles && cudaMemcpyAsync(d_angles, angles, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess)) {
+      fail("hgsfa_crop_extent: host-to-device copy failed");
+      break;
+    }
+    if (hgsfa_crop_extent_device(d_img, H, W, d_boxes, d_angles, n, ow, oh, filter, d_out, out_dtype, HGSFA_ROWMAJOR, st))
+      break;
+    if (cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      fail("hgsfa_crop_extent: device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    rc = 0;
+  } while (0);
+  cudaFree(d_img); cudaFree(d_boxes); cudaFree(d_angles); cudaFree(d_out);
+  return rc;
+}

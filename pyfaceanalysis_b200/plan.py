@@ -1,0 +1,657 @@
+"""Flow compiler: unpickled MDP / cuicuilco node graph -> fused layer operations -> plan blob.
+
+The reference executes a flow node by node (``mdp.Flow.execute``; call sites
+``FaceDetectUpdated.py:699``, ``face_analysis.py:1064,1257``): every Switchboard materialises a gathered
+copy of the whole activation matrix, every Layer loops over its nodes in Python, every expansion
+allocates temporaries.  Here the graph is lowered once, on the host and in
+float64, to a short list of *layer operations* the CUDA kernels in ``csrc/flow.cu`` execute:
+
+    op    = (gather index per node, input offset per node, passes)
+    pass  = (expansion term table, W[node], b[node], destination)
+
+* Switchboards / HeadNodes / IdentityNodes never run: they compose into the gather index of the next op.
+* PCANode / WhiteningNode / SFANode / LinearRegressionNode become one pass with an identity table
+  (the mean is subtracted at the operand fetch, ``in_offset``).
+* GeneralExpansionNode becomes the term table of the following projection.
+* iGSFANode (IEVMLRecNode) becomes either two passes -- slow features ``S = E @ W1 + b1`` kept in
+  shared memory, then ``R = [x0 | S] @ W2 + b2`` with the linear-regression reconstruction folded into
+  ``W2 = [V ; -beta V]`` -- or a single folded pass ``Y = E' @ W + b``, whichever executes fewer flops.
+
+All folding is done in float64; weights are rounded to float32 once, when the blob is written.
+"""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+from . import expansions as ex
+
+KC = 16          # rows per expansion chunk (csrc/flow.cu)
+TILE = 128
+MAX_PASSES = 4
+DST_GLOBAL, DST_ROWS = 1, 2
+
+# (WM, WN, NT) per cfg code, see run_pass<> in csrc/flow.cu
+CFG = {0: (4, 1, 16), 1: (2, 2, 16), 2: (1, 4, 16), 3: (1, 4, 32)}
+
+_SWITCHBOARDS = ("Switchboard", "Rectangular2dSwitchboard", "PInvSwitchboard", "DoubleRect2dSwitchboard",
+                 "DoubleRhomb2dSwitchboard", "MeanInverseSwitchboard", "ChannelSwitchboard")
+_LAYERS = ("Layer", "CloneLayer")
+_LINEAR = ("PCANode", "WhiteningNode", "SFANode", "GSFANode", "LinearRegressionNode")
+_IGSFA = ("iGSFANode", "IEVMLRecNode")
+
+
+class UnsupportedFlow(NotImplementedError):
+    pass
+
+
+def _cls(node):
+    return type(node).__name__
+
+
+def _get(node, *names, default=None):
+    for n in names:
+        v = getattr(node, n, None)
+        if v is not None:
+            return v
+    return default
+
+
+def _f64(a):
+    return np.asarray(a, dtype=np.float64)
+
+
+def node_input_dim(node):
+    d = _get(node, "_input_dim", "input_dim")
+    if d is None:
+        raise UnsupportedFlow("node %s carries no input_dim" % _cls(node))
+    return int(d)
+
+
+def flow_nodes(flow):
+    nodes = getattr(flow, "flow", None)
+    if nodes is None:
+        nodes = list(flow)
+    return list(nodes)
+
+
+# --------------------------------------------------------------------------------------------------
+# per-node lowering
+# --------------------------------------------------------------------------------------------------
+def _linear_params(node):
+    """(avg or None, W (d x m), b (m,)) with  y = (x - avg) @ W + b  (avg None: y = x @ W + b)."""
+    c = _cls(node)
+    out_dim = _get(node, "output_dim", "_output_dim")
+    if c in ("PCANode", "WhiteningNode"):
+        v = _f64(node.v)
+        if out_dim is not None:
+            v = v[:, :int(out_dim)]
+        return _f64(node.avg).reshape(-1), v, np.zeros(v.shape[1])
+    if c in ("SFANode", "GSFANode"):
+        sf = _f64(node.sf)
+        if out_dim is not None:
+            sf = sf[:, :int(out_dim)]
+        bias = _get(node, "_bias")
+        avg = _get(node, "avg")
+        if bias is None:
+            return _f64(avg).reshape(-1), sf, np.zeros(sf.shape[1])
+        bias = _f64(bias).reshape(-1)[:sf.shape[1]]
+        if avg is not None:
+            avg = _f64(avg).reshape(-1)
+            if np.allclose(avg @ sf, bias, rtol=1e-9, atol=1e-9 * (1.0 + np.abs(bias).max(initial=0.0))):
+                return avg, sf, np.zeros(sf.shape[1])   # subtract the mean first: better conditioned in fp32
+        return None, sf, -bias
+    if c == "LinearRegressionNode":
+        beta = _f64(node.beta)
+        if _get(node, "with_bias", default=True):
+            return None, beta[1:], beta[0].copy()
+        return None, beta, np.zeros(beta.shape[1])
+    raise UnsupportedFlow("no linear lowering for node class %r" % c)
+
+
+class _Pass(object):
+    """One projection of one node: term table over sources, W (K x N), b (N), destination."""
+
+    def __init__(self, terms, W, b, to_global, col_off=0, to_rows=False):
+        self.terms = terms          # TERM_DTYPE array, indices are *source* indices
+        self.W = W
+        self.b = b
+        self.to_global = to_global
+        self.to_rows = to_rows
+        self.col_off = col_off
+        self.row0 = -1              # assigned at layer assembly
+
+
+class _NodeProgram(object):
+    def __init__(self, d_in):
+        self.d_in = d_in
+        self.offset = np.zeros(d_in)
+        self.passes = []
+        self.out_dim = 0
+        self.alg_flops = 0
+
+
+def _identity_terms(sources):
+    t = np.zeros(len(sources), dtype=ex.TERM_DTYPE)
+    t["op"] = ex.OP_ID
+    t["i"] = np.asarray(sources, dtype=np.int64)
+    return t
+
+
+def _remap_terms(terms, sources):
+    """Terms written over a local vector -> terms over global source indices."""
+    src = np.asarray(sources, dtype=np.int64)
+    out = terms.copy()
+    out["i"] = src[terms["i"]]
+    two = (terms["op"] == ex.OP_MUL) | (terms["op"] == ex.OP_MUL3)
+    out["j"][two] = src[terms["j"][two]]
+    three = terms["op"] == ex.OP_MUL3
+    if three.any():
+        out["p"][three] = src[terms["p"][three].astype(np.int64)].astype(np.float32)
+    return out
+
+
+class _Lowerer(object):
+    """Lowers the node sequence applied to ONE receptive field (one child of a Layer)."""
+
+    def __init__(self, d_in, igsfa_mode="auto", j_pad=None):
+        self.prog = _NodeProgram(d_in)
+        self.cur = list(range(d_in))   # source index of every component of the current vector
+        self.cur_is_input = True
+        self.pending = None            # term table over the current vector (from an expansion node)
+        self.n_rows = 0
+        self.igsfa_mode = igsfa_mode
+        self.j_pad = j_pad
+        self.igsfa_J = []
+
+    # -- helpers
+    def _new_rows(self, n):
+        """Shared-memory rows for an intermediate result of width n.  The producing pass stores its
+        padded width (``_choose_cfg``), so the allocation advances by that."""
+        r0 = self.n_rows
+        self.n_rows += _choose_cfg(n)[1]
+        return [self.prog.d_in + r0 + k for k in range(n)], r0
+
+    def _shift_current(self, mean):
+        """current vector <- current vector - mean."""
+        mean = _f64(mean).reshape(-1)
+        if self.pending is not None:
+            raise UnsupportedFlow("mean subtraction after an un-projected expansion")
+        if self.cur_is_input:
+            self.prog.offset[np.asarray(self.cur)] += mean
+        else:
+            last = self.prog.passes[-1]
+            last.b = last.b - mean
+
+    def _emit(self, terms, W, b, final, col_off=0, also_rows=False):
+        p = _Pass(terms, W, b, to_global=final, col_off=col_off, to_rows=(not final) or also_rows)
+        self.prog.passes.append(p)
+        return p
+
+    # -- node kinds
+    def linear(self, node, final):
+        avg, W, b = _linear_params(node)
+        d = len(self.cur) if self.pending is None else len(self.pending)
+        if W.shape[0] != d:
+            raise ValueError("%s: x has dimension %d, should be %d" % (_cls(node), d, W.shape[0]))
+        if avg is not None:
+            if self.pending is None:
+                self._shift_current(avg)
+            else:
+                b = b - avg @ W    # mean of the expanded vector: fold
+        terms = _identity_terms(self.cur) if self.pending is None else self.pending
+        self.pending = None
+        self.prog.alg_flops += 2 * W.shape[0] * W.shape[1] + (W.shape[0] if avg is not None else W.shape[1])
+        self._emit(terms, W, b, final)
+        if not final:
+            self.cur, r0 = self._new_rows(W.shape[1])
+            self.prog.passes[-1].row0 = r0
+            self.cur_is_input = False
+        else:
+            self.prog.out_dim = W.shape[1]
+
+    def expansion(self, node):
+        if self.pending is not None:
+            raise UnsupportedFlow("two consecutive expansions without a projection")
+        funcs = list(node.funcs)
+        local = ex.lower(funcs, len(self.cur))
+        self.prog.alg_flops += ex.term_flops(local)
+        self.pending = _remap_terms(local, self.cur)
+
+    def igsfa(self, node, final):
+        if not final:
+            raise UnsupportedFlow("an iGSFA node must be the last node of its receptive field")
+        if self.pending is not None:
+            raise UnsupportedFlow("iGSFA node after an un-projected expansion")
+        d = len(self.cur)
+        self._shift_current(node.x_mean)
+        x_src = list(self.cur)
+        p_src = x_src
+        pre = _get(node, "pre_expansion_node")
+        self.prog.alg_flops += d
+        if pre is not None:
+            if _cls(pre) not in _LINEAR:
+                raise UnsupportedFlow("iGSFA pre_expansion_node of class %r" % _cls(pre))
+            self.linear(pre, final=False)
+            p_src = list(self.cur)
+        expn = _get(node, "exp_node")
+        if expn is not None:
+            local = ex.lower(list(expn.funcs), len(p_src))
+            self.prog.alg_flops += ex.term_flops(local)
+            T = _remap_terms(local, p_src)
+        else:
+            T = _identity_terms(p_src)
+        D = len(T)
+        J = int(node.num_sfa_features_preserved)
+        avg_s, sf, b_s = _linear_params(node.sfa_node)
+        if sf.shape[0] != D:
+            raise ValueError("iGSFA sfa_node: expanded dimension %d, should be %d" % (D, sf.shape[0]))
+        if avg_s is not None:
+            b_s = b_s - avg_s @ sf
+        self.prog.alg_flops += 2 * D * sf.shape[1] + sf.shape[1]
+        magn = _f64(_get(node, "magn_n_sfa_x", default=1.0)).reshape(-1)
+        magn = np.broadcast_to(magn, (sf.shape[1],)) if magn.size == 1 else magn[:sf.shape[1]]
+        W1 = sf[:, :J] * magn[:J]
+        b1 = b_s[:J] * magn[:J]
+        self.prog.alg_flops += J
+        pca = _get(node, "pca_node")
+        if pca is None:
+            self._emit(T, W1, b1, final=True)
+            self.prog.out_dim = J
+            self.igsfa_J.append(J)
+            return
+        avg_p, V, b_p = _linear_params(pca)
+        if V.shape[0] != d:
+            raise ValueError("iGSFA pca_node: dimension %d, should be %d" % (d, V.shape[0]))
+        if avg_p is None:
+            avg_p = np.zeros(d)
+        P = V.shape[1]
+        recon = bool(_get(node, "reconstruct_with_sfa", default=True)) and J > 0
+        if recon:
+            _, B, b0 = _linear_params(node.lr_node)      # x_app = s_n @ B + b0
+            if B.shape != (J, d):
+                raise ValueError("iGSFA lr_node: beta maps %s, expected (%d, %d)" % (B.shape, J, d))
+            self.prog.alg_flops += 2 * J * d + d
+        else:
+            B, b0 = np.zeros((J, d)), np.zeros(d)
+        self.prog.alg_flops += 2 * d + 2 * d * P
+        M2 = -(B @ V)                                    # (J x P): contribution of s_n to the residual part
+        c2 = b_p - (b0 + avg_p) @ V
+        self.prog.out_dim = J + P
+        self.igsfa_J.append(J)
+
+        jp = self.j_pad if self.j_pad is not None else J
+
+        def padded(k, n):   # what the kernel executes: K rounded to the chunk, N to the register tile
+            return 2 * (-(-k // KC) * KC) * _choose_cfg(n)[1]
+
+        cost_two = padded(D, jp) + padded(d + (jp if recon else 0), P)
+        # identity rows the folded form can reuse (only when the expansion reads x0 directly)
+        id_row = {}
+        if p_src is x_src or p_src == x_src:
+            for k in range(D):
+                if T["op"][k] == ex.OP_ID and int(T["i"][k]) not in id_row:
+                    id_row[int(T["i"][k])] = k
+        missing = [s for s in x_src if s not in id_row]
+        cost_fold = padded(D + len(missing), J + P) if J + P <= 128 else float("inf")
+        mode = self.igsfa_mode
+        if mode == "auto":
+            mode = "fold" if cost_fold <= 1.1 * cost_two else "two_pass"
+        if mode == "fold":
+            Tf = np.concatenate([T, _identity_terms(missing)]) if missing else T
+            Wf = np.zeros((len(Tf), J + P))
+            Wf[:D, :J] = W1
+            Wf[:D, J:] = W1 @ M2
+            for s_i, s in enumerate(x_src):
+                row = id_row[s] if s in id_row else D + missing.index(s)
+                Wf[row, J:] += V[s_i]
+            bf = np.concatenate([b1, b1 @ M2 + c2])
+            self._emit(Tf, Wf, bf, final=True)
+        else:
+            pa = self._emit(T, W1, b1, final=True, col_off=0, also_rows=recon)
+            pa.n_keep = J
+            if recon:
+                s_rows, r0 = self._new_rows(jp)
+                pa.row0 = r0
+                pa.pad_to = jp
+                T2 = _identity_terms(x_src + s_rows)
+                W2 = np.zeros((d + jp, P))
+                W2[:d] = V
+                W2[d:d + J] = M2
+            else:
+                T2 = _identity_terms(x_src)
+                W2 = V
+            self._emit(T2, W2, c2, final=True, col_off=J)
+        self.mode_used = mode
+
+    def run(self, nodes):
+        for k, node in enumerate(nodes):
+            final = k == len(nodes) - 1
+            c = _cls(node)
+            if c == "FlowNode":
+                raise UnsupportedFlow("nested FlowNode inside a FlowNode")
+            if c in _LINEAR:
+                self.linear(node, final)
+            elif c == "GeneralExpansionNode":
+                if final:
+                    raise UnsupportedFlow("an expansion must be followed by a projection inside its layer")
+                self.expansion(node)
+            elif c in _IGSFA:
+                self.igsfa(node, final)
+            elif c == "IdentityNode":
+                if final:
+                    raise UnsupportedFlow("trailing IdentityNode in a receptive field")
+            else:
+                raise UnsupportedFlow("no lowering for node class %r (pyfaceanalysis_b200/plan.py)" % c)
+        return self.prog
+
+
+def _child_sequence(child):
+    if _cls(child) == "FlowNode":
+        return flow_nodes(_get(child, "_flow", "flow"))
+    return [child]
+
+
+# --------------------------------------------------------------------------------------------------
+# layer assembly
+# --------------------------------------------------------------------------------------------------
+class OpSpec(object):
+    """One fused layer operation (host description; ``tests/plan_interp.py`` can execute it in numpy)."""
+
+    def __init__(self):
+        self.n_nodes = 0
+        self.d_in = 0
+        self.in_dim = 0
+        self.out_dim = 0
+        self.shared = False
+        self.gather = None      # (n_nodes, d_in) int32
+        self.in_offset = None   # (n_w, d_in) float64
+        self.out_col = None     # (n_nodes,) int32
+        self.passes = []        # list of dict(terms, W (n_w,K,Npad), b (n_w,Npad), dst, row0, cfg, n_valid, col_off, K_real, N_real)
+        self.n_rows = 0
+        self.twc = 1
+        self.alg_flops = 0
+        self.exe_flops = 0
+        self.mode = ""
+        self.clip = (-np.inf, np.inf)   # saturation applied when results are stored to the output buffer
+
+
+def _choose_cfg(n_real):
+    if n_real <= 16:
+        return 0, 16
+    if n_real <= 32:
+        return 1, 32
+    if n_real <= 64:
+        return 2, -(-n_real // 16) * 16
+    if n_real <= 128:
+        return 3, -(-n_real // 32) * 32
+    raise UnsupportedFlow("a projection with %d output columns per node (max 128)" % n_real)
+
+
+def _assemble_layer(children, gather_cols, in_dim, igsfa_mode="auto"):
+    """children: list of node sequences (one per receptive field); gather_cols: list of index arrays."""
+    n_nodes = len(children)
+    d_in = len(gather_cols[0])
+    if any(len(g) != d_in for g in gather_cols):
+        raise UnsupportedFlow("a Layer whose nodes have different input dimensions")
+    shared = all(all(a is b for a, b in zip(children[0], ch)) and len(ch) == len(children[0]) for ch in children)
+    uniq = [children[0]] if shared else children
+
+    # iGSFA nodes of one layer keep different numbers of slow features: pad to the layer maximum
+    j_pad = None
+    js = [int(n.num_sfa_features_preserved) for ch in uniq for n in ch if _cls(n) in _IGSFA]
+    if js:
+        j_pad = max(js)
+
+    def lower_all(mode):
+        progs = []
+        for ch in uniq:
+            lw = _Lowerer(d_in, igsfa_mode=mode, j_pad=j_pad)
+            progs.append((lw.run(ch), lw))
+        return progs
+
+    progs = lower_all(igsfa_mode)
+    if igsfa_mode == "auto":
+        modes = set(getattr(lw, "mode_used", None) for _, lw in progs) - {None}
+        if len(modes) > 1:   # nodes disagree: take the majority for the whole layer
+            votes = [getattr(lw, "mode_used", None) for _, lw in progs]
+            pick = max(modes, key=votes.count)
+            progs = lower_all(pick)
+    n_pass = len(progs[0][0].passes)
+    if any(len(p.passes) != n_pass for p, _ in progs):
+        raise UnsupportedFlow("nodes of one Layer lower to different pass counts")
+    if n_pass > MAX_PASSES:
+        raise UnsupportedFlow("a receptive field needs %d passes (max %d)" % (n_pass, MAX_PASSES))
+
+    op = OpSpec()
+    op.n_nodes, op.d_in, op.in_dim, op.shared = n_nodes, d_in, in_dim, shared
+    op.gather = np.asarray(gather_cols, dtype=np.int32).reshape(n_nodes, d_in)
+    op.in_offset = np.stack([p.offset for p, _ in progs])
+    out_dims = [p.out_dim for p, _ in progs]
+    if shared:
+        out_dims = out_dims * n_nodes
+    op.out_col = np.concatenate([[0], np.cumsum(out_dims)[:-1]]).astype(np.int32)
+    op.out_dim = int(np.sum(out_dims))
+    op.mode = getattr(progs[0][1], "mode_used", "")
+    op.alg_flops = int(sum(p.alg_flops for p, _ in progs) * (n_nodes if shared else 1))
+
+    row_cursor = 0
+    max_wm = 1
+    for k in range(n_pass):
+        plist = [p.passes[k] for p, _ in progs]
+        t0 = plist[0].terms
+        for q in plist[1:]:
+            if len(q.terms) != len(t0) or not np.array_equal(q.terms, t0):
+                raise UnsupportedFlow("nodes of one Layer use different expansion tables")
+        K_real = len(t0)
+        K = -(-K_real // KC) * KC
+        n_real = max(q.W.shape[1] for q in plist)
+        to_rows = plist[0].to_rows
+        pad_to = max([getattr(q, "pad_to", 0) for q in plist] + [n_real]) if to_rows else n_real
+        cfg, npad = _choose_cfg(max(n_real, pad_to))
+        terms = np.zeros(K, dtype=ex.TERM_DTYPE)
+        terms[:K_real] = t0
+        terms["i"][K_real:] = t0["i"][0] if K_real else 0   # padded rows: any valid source, zero weights
+        n_w = len(plist)
+        W = np.zeros((n_w, K, npad))
+        b = np.zeros((n_w, npad))
+        n_valid = np.zeros(n_nodes, dtype=np.int32)
+        col_off = np.zeros(n_nodes, dtype=np.int32)
+        for w_i, q in enumerate(plist):
+            W[w_i, :K_real, :q.W.shape[1]] = q.W
+            b[w_i, :q.W.shape[1]] = q.b
+        for nd in range(n_nodes):
+            q = plist[0 if shared else nd]
+            n_valid[nd] = getattr(q, "n_keep", q.W.shape[1]) if q.to_global else 0
+            col_off[nd] = q.col_off
+        dst = (DST_GLOBAL if plist[0].to_global else 0) | (DST_ROWS if to_rows else 0)
+        row0 = 0
+        if to_rows:
+            # rows are allocated in emission order by the lowerer; both sides must agree
+            row0 = row_cursor
+            if any(q.row0 != row0 for q in plist):
+                raise UnsupportedFlow("nodes of one Layer produce intermediate results of different widths")
+            row_cursor += npad
+        op.passes.append(dict(terms=terms, W=W, b=b, dst=dst, row0=row0, cfg=cfg, n_valid=n_valid,
+                              col_off=col_off, K_real=K_real, N_real=n_real, K=K, Npad=npad))
+        max_wm = max(max_wm, CFG[cfg][0])
+        op.exe_flops += n_nodes * 2 * K * npad
+    op.n_rows = row_cursor
+    op.twc = max_wm
+    return op
+
+
+# --------------------------------------------------------------------------------------------------
+# flow-level compiler
+# --------------------------------------------------------------------------------------------------
+class PlanSpec(object):
+    def __init__(self, input_dim):
+        self.input_dim = int(input_dim)
+        self.output_dim = int(input_dim)
+        self.ops = []
+        self.out_cols = None   # columns of the last op's buffer that form the flow output (None = all)
+
+    @property
+    def alg_flops(self):
+        return sum(op.alg_flops for op in self.ops)
+
+    @property
+    def exe_flops(self):
+        return sum(op.exe_flops for op in self.ops)
+
+
+def compile_flow(flow, input_dim=None, igsfa_mode="auto"):
+    """Lower a flow (object with ``.flow`` or a sequence of nodes) to a :class:`PlanSpec`."""
+    nodes = flow_nodes(flow)
+    if not nodes:
+        raise UnsupportedFlow("empty flow")
+    if input_dim is None:
+        input_dim = node_input_dim(nodes[0])
+    spec = PlanSpec(input_dim)
+    cols = np.arange(input_dim, dtype=np.int64)   # logical column -> column of the last materialised buffer
+    buf_dim = input_dim
+    pending_layers = []   # per-field node sequences collected from consecutive aligned Layers
+
+    def flush_pending():
+        nonlocal cols, buf_dim, pending_layers
+        if not pending_layers:
+            return
+        fields, gathers = pending_layers
+        op = _assemble_layer(fields, gathers, buf_dim, igsfa_mode)
+        spec.ops.append(op)
+        buf_dim = op.out_dim
+        cols = np.arange(buf_dim, dtype=np.int64)
+        pending_layers = []
+
+    def add_layer(children):
+        """children: list of child nodes, consuming consecutive slices of the current logical vector."""
+        nonlocal pending_layers
+        dims = [node_input_dim(ch) for ch in children]
+        if sum(dims) != len(cols):
+            raise ValueError("%s: x has dimension %d, should be %d" % ("Layer", len(cols), sum(dims)))
+        seqs = [_child_sequence(ch) for ch in children]
+        if pending_layers:
+            # a Layer directly after an expansion-only Layer with the same partition: fuse per field
+            fields, gathers = pending_layers
+            if len(fields) != len(seqs):
+                raise UnsupportedFlow("expansion Layer followed by a Layer with a different partition")
+            fields = [f + s for f, s in zip(fields, seqs)]
+            pending_layers = [fields, gathers]
+        else:
+            starts = np.concatenate([[0], np.cumsum(dims)[:-1]])
+            gathers = [cols[s:s + d] for s, d in zip(starts, dims)]
+            pending_layers = [seqs, gathers]
+        # keep collecting only while every field still ends in an un-projected expansion
+        if not all(_cls(f[-1]) == "GeneralExpansionNode" for f in pending_layers[0]):
+            flush_pending()
+
+    for node in nodes:
+        c = _cls(node)
+        if c in _SWITCHBOARDS or (hasattr(node, "connections") and not hasattr(node, "nodes")):
+            if pending_layers:
+                raise UnsupportedFlow("Switchboard directly after an expansion Layer")
+            conn = np.asarray(node.connections, dtype=np.int64)
+            if conn.size and (conn.min() < 0 or conn.max() >= len(cols)):
+                raise ValueError("Switchboard: connection index outside the %d input columns" % len(cols))
+            cols = cols[conn]
+        elif c == "HeadNode":
+            if pending_layers:
+                raise UnsupportedFlow("HeadNode directly after an expansion Layer")
+            cols = cols[:int(_get(node, "output_dim", "_output_dim"))]
+        elif c == "IdentityNode":
+            continue
+        elif c == "PointwiseFunctionNode":
+            # element-wise saturation: fused into the epilogue of the producing op
+            name = ex.func_name(node.func)
+            lim = ex.clip_limit(name)
+            if lim is None:
+                raise UnsupportedFlow("PointwiseFunctionNode with function %r (only clip_<L>)" % name)
+            if pending_layers:
+                raise UnsupportedFlow("a clipping node directly after an expansion Layer")
+            if not spec.ops:
+                # nothing materialised yet (a clip node executed on its own): saturate in a copy op
+                spec.ops.append(_copy_op(cols, buf_dim))
+                buf_dim = spec.ops[-1].out_dim
+                cols = np.arange(buf_dim, dtype=np.int64)
+            lo, hi = spec.ops[-1].clip
+            spec.ops[-1].clip = (max(lo, -lim), min(hi, lim))
+        elif c in _LAYERS:
+            add_layer(list(node.nodes))
+        elif c == "SameInputLayer":
+            raise UnsupportedFlow("SameInputLayer")
+        else:
+            add_layer([node])
+    if pending_layers:
+        raise UnsupportedFlow("flow ends with an expansion that is never projected")
+    spec.output_dim = len(cols)
+    if not spec.ops or not np.array_equal(cols, np.arange(len(cols))):
+        # the flow ends in (or consists of) a gather: materialise it with identity projections over
+        # 16-column receptive fields (a Switchboard executed on its own, e.g. through a node facade)
+        spec.ops.append(_copy_op(cols, buf_dim))
+    return spec
+
+
+def _copy_op(cols, in_dim):
+    n = len(cols)
+    n_nodes = -(-n // 16)
+    gather = np.zeros((n_nodes, 16), dtype=np.int32)
+    flat = np.concatenate([cols, np.full(n_nodes * 16 - n, cols[-1] if n else 0)])
+    gather[:] = flat.reshape(n_nodes, 16)
+    op = OpSpec()
+    op.n_nodes, op.d_in, op.in_dim, op.out_dim, op.shared = n_nodes, 16, int(in_dim), n, True
+    op.gather = gather
+    op.in_offset = np.zeros((1, 16))
+    op.out_col = (np.arange(n_nodes) * 16).astype(np.int32)
+    n_valid = np.full(n_nodes, 16, dtype=np.int32)
+    n_valid[-1] = n - 16 * (n_nodes - 1)
+    op.passes = [dict(terms=_identity_terms(range(16)), W=np.eye(16)[None], b=np.zeros((1, 16)), dst=DST_GLOBAL,
+                      row0=0, cfg=0, n_valid=n_valid, col_off=np.zeros(n_nodes, dtype=np.int32), K_real=16,
+                      N_real=16, K=16, Npad=16)]
+    op.n_rows, op.twc, op.mode = 0, 4, "copy"
+    op.exe_flops = n_nodes * 2 * 16 * 16
+    return op
+
+
+# --------------------------------------------------------------------------------------------------
+# blob writer (format parsed by hgsfa_plan_create, csrc/flow.cu)
+# --------------------------------------------------------------------------------------------------
+def _pad16(b):
+    return b + b"\0" * ((-len(b)) % 16)
+
+
+def _arr(a, dtype):
+    return _pad16(np.ascontiguousarray(a, dtype=dtype).tobytes())
+
+
+def serialize(spec):
+    last_dim = spec.ops[-1].out_dim
+    out = [b"HGSFAPL1" + struct.pack("<7q", spec.input_dim, last_dim, len(spec.ops), 0, 0, 0, 0)]
+    assert len(out[0]) == 64
+    for op in spec.ops:
+        hdr = [op.n_nodes, op.d_in, op.in_dim, op.out_dim, len(op.passes), int(op.shared), op.n_rows, op.twc,
+               op.alg_flops, op.exe_flops, 0, 0]
+        out.append(struct.pack("<12q", *hdr) + struct.pack("<4d", float(op.clip[0]), float(op.clip[1]), 0.0, 0.0))
+        out.append(_arr(op.gather, np.int32))
+        out.append(_arr(op.in_offset, np.float32))
+        out.append(_arr(op.out_col, np.int32))
+        for ps in op.passes:
+            out.append(struct.pack("<8q", ps["K"], ps["Npad"], ps["dst"], ps["row0"], ps["cfg"], ps["K_real"],
+                                   ps["N_real"], 0))
+            out.append(_arr(ps["terms"], ex.TERM_DTYPE))
+            out.append(_arr(ps["W"], np.float32))
+            out.append(_arr(ps["b"], np.float32))
+            out.append(_arr(ps["n_valid"], np.int32))
+            out.append(_arr(ps["col_off"], np.int32))
+    return b"".join(out)
+
+
+def describe(spec):
+    lines = ["plan: %d -> %d, %d ops, %.3f MFLOP/window algorithmic, %.3f executed"
+             % (spec.input_dim, spec.output_dim, len(spec.ops), spec.alg_flops / 1e6, spec.exe_flops / 1e6)]
+    for k, op in enumerate(spec.ops):
+        ps = ", ".join("K%d->N%d(cfg%d)" % (p["K_real"], p["N_real"], p["cfg"]) for p in op.passes)
+        lines.append("  op%-2d nodes=%-4d d_in=%-4d out=%-5d %s %s [%s] twc=%d rows=%d"
+                     % (k, op.n_nodes, op.d_in, op.out_dim, "clone" if op.shared else "layer", op.mode, ps,
+                        op.twc, op.n_rows))
+    return "\n".join(lines)

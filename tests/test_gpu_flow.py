@@ -1,0 +1,97 @@
+"""GPU parity of the flow forward (csrc/flow.cu through the C ABI) against the float64 oracle.
+
+Tolerance (BASELINE.json north_star): max |err| <= 1e-3 x per-feature std, written below as TOL.
+"""
+import numpy as np
+import pytest
+
+from oracle import nodes as onodes
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _check(gflow, flow, x, std=None, tol=TOL):
+    y_ref = onodes.flow_execute(flow, x.astype(np.float64))
+    y = gflow.execute(x)
+    assert y.dtype == np.float64 and y.shape == y_ref.shape
+    if std is None:
+        std = y_ref.std(axis=0)
+    err = np.abs(y - y_ref) / std
+    assert np.isfinite(y).all()
+    assert err.max() <= tol, "max err/std %.3g" % err.max()
+    return err.max()
+
+
+@pytest.mark.parametrize("mode", ["auto", "fold", "two_pass"])
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 700])
+def test_tiny_flow_parity(tiny_flow, mode, n):
+    from pyfaceanalysis_b200 import GpuFlow, synthetic
+    g = GpuFlow(tiny_flow, igsfa_mode=mode)
+    x = synthetic.synthetic_patches(n, (16, 16), 100 + n)
+    ref_std = onodes.flow_execute(tiny_flow, synthetic.synthetic_patches(500, (16, 16), 7).astype(np.float64)).std(axis=0)
+    for dt in (np.uint8, np.float32, np.float64):
+        _check(g, tiny_flow, x.astype(dt), std=ref_std)
+    g.close()
+
+
+def test_empty_and_bad_dim(tiny_flow):
+    from pyfaceanalysis_b200 import GpuFlow
+    g = GpuFlow(tiny_flow)
+    assert g.execute(np.zeros((0, 256))).shape == (0, 16)
+    with pytest.raises(ValueError):
+        g.execute(np.zeros((3, 255)))
+    g.close()
+
+
+def test_u11l_parity_in_distribution(u11l_flow):
+    from pyfaceanalysis_b200 import GpuFlow, synthetic
+    g = GpuFlow(u11l_flow)
+    x = synthetic.synthetic_patches(600, (64, 64), 11)
+    e = _check(g, u11l_flow, x, std=u11l_flow._train_output_std)
+    print("U11L_64 in-distribution max err/std", e)
+    # feature slice (the caller's sl[:, 0:D]) and float32 output
+    y9 = g.execute(x[:50], n_features=9, out_dtype=np.float32)
+    yall = g.execute(x[:50])
+    assert y9.shape == (50, 9) and np.allclose(y9, yall[:, :9], rtol=1e-6, atol=1e-4)
+    g.close()
+
+
+def test_u11l_parity_uniform_noise(u11l_flow):
+    """BASELINE config 2 input: uniform integer pixels 0..255 (far outside the fitted distribution; the
+    inter-layer saturation keeps the network finite)."""
+    from pyfaceanalysis_b200 import GpuFlow
+    g = GpuFlow(u11l_flow)
+    rng = np.random.default_rng(12345600)
+    x = rng.integers(0, 256, (512, 4096), dtype=np.uint8)
+    _check(g, u11l_flow, x)
+    g.close()
+
+
+def test_chunking_is_invisible(u11l_flow):
+    """Front/back chunk sizes (workspace tiling) must not change results; exercises several chunks."""
+    from pyfaceanalysis_b200 import GpuFlow, synthetic
+    x = synthetic.synthetic_patches(1500, (64, 64), 21)
+    g = GpuFlow(u11l_flow)
+    y0 = g.execute(x)
+    g.set_chunks(front=512, back=1024)
+    y1 = g.execute(x)
+    assert np.array_equal(y0, y1)
+    g.close()
+
+
+def test_node_facades(tiny_flow):
+    from pyfaceanalysis_b200 import GpuFlow, synthetic
+    g = GpuFlow(tiny_flow)
+    x = synthetic.synthetic_patches(40, (16, 16), 5).astype(np.float64)
+    cur_ref = x
+    cur = x
+    for k, node in enumerate(g):
+        cur_ref = onodes.execute(onodes.flow_nodes(tiny_flow)[k], cur_ref)
+        cur = node.execute(cur)
+        assert cur.shape == cur_ref.shape
+        scale = max(1.0, np.abs(cur_ref).max())
+        assert np.abs(cur - cur_ref).max() <= 2e-5 * scale, (k, type(node.node).__name__)
+    part = g.execute(x, nodenr=1)
+    assert np.abs(part - onodes.flow_execute(tiny_flow, x, nodenr=1)).max() < 1e-2
+    g.close()
