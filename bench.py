@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Headline benchmark: HiGSFA flow windows/s (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): forward pass of the FaceCentering2-shaped flow -- the synthetic
+11-layer "ultra thin" HiGSFA network U11L_64 (pyfaceanalysis_b200/synthetic.py; the shipped flow pickles
+were stripped from the reference) -- over a batch of 1 048 576 windows of 64x64 = 4096 uint8 pixels,
+uniform integers 0..255, seed 12345600 (FaceDetectUpdated.py:146).  One step = one such batch per GPU.
+
+  value : windows/s with the (N, 4096) uint8 window matrix already resident in HBM (row-major, as the
+          reference hands it over); timed with CUDA events on the launching stream, max over ranks
+  e2e   : the same through the public drop-in call GpuFlow.execute(x) with x in pinned HOST memory:
+          host->device copy of the windows and device->host copy of the (N, 60) float64 features are
+          inside the timed region
+  roofline : the fused layer kernels are FP32-FFMA bound; achieved =
+          algorithmic flops (hgsfa_plan_flops) / device time of the layer launches
+  cpu_baseline : the float64 numpy oracle (the reference cannot run: Python 2 + un-vendored mdp /
+          cuicuilco) on a bounded sample on the box's host cores, BLAS threads = min(12, nproc)
+          (FaceDetectUpdated.py:74)
+
+Multi-GPU: windows are independent -> every rank processes its own batch (weak scaling), no collective
+on the data path; torch.distributed is used only for the barrier and the max-over-ranks of the time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_WINDOWS = 1 << 20
+SEED = 12345600
+FLOW_SPEC = "U11L_64"
+METRIC = "HiGSFA flow windows/sec"
+UNIT = "windows/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        p["_source"] = "MEASURED_PEAKS.json"
+        return p
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "_source": "fallback (B200_PROFILING.md)"}
+
+
+def _fp32_peak():
+    """Measured FFMA peak of this pool's B200 (tools/microbench.cu, profiles/microbench_r01.json)."""
+    path = os.path.join(ROOT, "profiles", "microbench_r01.json")
+    try:
+        with open(path) as f:
+            m = json.load(f)
+        return float(m["ffma2_tflops"]), "profiles/microbench_r01.json (fma.rn.f32x2, measured on this pool)"
+    except Exception:
+        return 74.4, "nominal 148 SM x 128 FMA x 2 x 1.965 GHz"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    c = [v.strip() for v in line.split(",")]
+                    if len(c) < 9:
+                        continue
+                    try:
+                        sm.append(float(c[1]))
+                        smax.append(float(c[2]))
+                    except ValueError:
+                        continue
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                       c[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def cpu_oracle_windows_per_s(flow, n_sample, threads, reps=1):
+    """The float64 numpy restatement (oracle/) on host cores: the 'port' CPU baseline."""
+    from oracle import nodes as onodes
+    from threadpoolctl import threadpool_limits
+    rng = np.random.default_rng(SEED)
+    x = rng.integers(0, 256, (n_sample, 4096), dtype=np.uint8).astype(np.float64)
+    with threadpool_limits(limits=threads):
+        onodes.flow_execute(flow, x[:256])      # warm caches / BLAS threads
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            onodes.flow_execute(flow, x)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return n_sample / best, best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm for this path (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    from pyfaceanalysis_b200 import synthetic
+    flow = synthetic.cached_flow(FLOW_SPEC, seed=0)
+    threads = min(12, os.cpu_count() or 1)
+    n_sample = 4096
+    from oracle import nodes as onodes
+    from threadpoolctl import threadpool_limits
+    rng = np.random.default_rng(SEED)
+    x = rng.integers(0, 256, (n_sample, 4096), dtype=np.uint8).astype(np.float64)
+    with threadpool_limits(limits=threads):
+        for _ in range(max(1, args.warmup)):
+            onodes.flow_execute(flow, x[:512])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            onodes.flow_execute(flow, x)
+        dt = time.perf_counter() - t0
+    value = n_sample * args.steps / dt
+    sample = "%d windows x 4096 px per step (uniform uint8, seed %d), float64 numpy oracle" % (n_sample, SEED)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "U11L_64 flow forward, bounded CPU sample of configs[1]", "windows_per_step": n_sample,
+                   "window_dim": 4096},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--windows", type=int, default=N_WINDOWS, help="windows per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pyfaceanalysis_b200 import GpuFlow, _lib, synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+
+    flow = synthetic.cached_flow(FLOW_SPEC, seed=0)
+    g = GpuFlow(flow, device=local_rank)
+    n = args.windows
+    F = g.output_dim
+
+    # ---- synthetic input, resident in HBM, row-major (N, 4096) uint8 ----
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(SEED + rank)
+    x_dev = torch.randint(0, 256, (n, g.input_dim), dtype=torch.uint8, device=dev, generator=gen)
+    y_dev = torch.empty((n, F), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        g.execute_torch(x_dev, out=y_dev)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    l0 = g.stats()["launches"]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.synchronize(dev)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_step_kernel_ms = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = g.stats()["launches"] - l0
+    kernel_ms_last = g.stats()["last_ms"]      # device time of the last step's launches (plan events)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API, host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        x_host = torch.empty((n, g.input_dim), dtype=torch.uint8).pin_memory()
+        x_host.copy_(x_dev)
+        y_host = torch.empty((n, F), dtype=torch.float64).pin_memory()
+        xh, yh = x_host.numpy(), y_host.numpy()
+        g.execute(xh, out=yh)
+        barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            g.execute(xh, out=yh)    # returns after the D2H copy of the features has completed
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * n * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * g.input_dim),
+               "d2h_bytes_per_step": int(n * F * 8), "steps": e2e_steps,
+               "api": "GpuFlow.execute(x_host_pinned_u8, out=y_host_pinned_f64)"}
+        # keep the parity honest inside the bench as well: device path == host path
+        chk = y_dev[:4096].double().cpu().numpy()
+        if not np.allclose(chk, yh[:4096], rtol=1e-5, atol=1e-3):
+            raise SystemExit("bench: device-resident and host-path results differ")
+        del x_host, y_host
+
+    if rank == 0:
+        fl = g.flops(n)
+        fp32_peak, fp32_src = _fp32_peak()
+        peaks = _peaks()
+        achieved_tflops = fl["algorithmic"] / (kernel_ms_last * 1e-3) / 1e12 if kernel_ms_last > 0 else None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: U11L_64 (FaceCentering2-shaped synthetic HiGSFA flow) forward, "
+                                   "%d windows x 4096 uint8 per GPU per step" % n,
+                       "windows_per_gpu": n, "window_dim": g.input_dim, "features": F, "flow": FLOW_SPEC,
+                       "input_layout": "row-major (N,4096) uint8 resident in HBM",
+                       "l2": "inputs (%.1f GB/step) far larger than the 126 MB L2; no flush needed" % (n * 4096 / 1e9),
+                       "parallelism": "windows sharded across GPUs, no collective"},
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                       "samples": clocks["samples"]},
+            "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": (achieved_tflops / fp32_peak) if achieved_tflops else None, "traffic": None,
+                         "kernel": "hgsfa::layer_kernel (all 11 layer launches of a step)",
+                         "algorithmic_flops_per_window": fl["algorithmic"] / n,
+                         "executed_flops_per_window": fl["executed"] / n,
+                         "kernel_ms_per_step": kernel_ms_last,
+                         "peak_source": fp32_src,
+                         "hbm_frac": (fl["min_bytes"] / (kernel_ms_last * 1e-3) / 1e9 / peaks["hbm_gbs"])
+                         if kernel_ms_last > 0 else None,
+                         "hbm_peak_source": peaks["_source"]},
+        }
+        if not args.no_cpu_baseline:
+            threads = min(12, os.cpu_count() or 1)
+            n_sample = 8192
+            v, secs = cpu_oracle_windows_per_s(flow, n_sample, threads)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": "%d windows x 4096 px (same distribution), float64 numpy oracle, %.1f s"
+                                             % (n_sample, secs)}
+        print(json.dumps(out))
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

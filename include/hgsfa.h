@@ -14,7 +14,9 @@
  *   - handles are not thread-safe; one handle per (object, device) (SURVEY.md 8b "Threading").
  *   - "host" entry points take host pointers and do the H2D / D2H copies themselves;
  *     "_device" entry points take device pointers on the handle's device.
- *   - stream arguments are cudaStream_t passed as void* (NULL = the handle's own stream).
+ *   - stream arguments are cudaStream_t passed as void*.  For "_device" entry points NULL is CUDA's
+ *     default stream; for host entry points NULL selects a stream owned by the handle (the call
+ *     returns only after its device-to-host copies have completed either way).
  */
 #ifndef HGSFA_H_
 #define HGSFA_H_

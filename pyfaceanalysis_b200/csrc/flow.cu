@@ -1,274 +1,26 @@
-// Fused HiGSFA layer kernels and the flow plan (sm_100a).
+// Flow plan: parses the plan blob written by pyfaceanalysis_b200/plan.py, owns the workspace and
+// schedules the fused layer kernels (csrc/layer.cuh) over window chunks (sm_100a).
 //
 // Replaces mdp.Flow.execute over hinet.Switchboard / Layer / CloneLayer nodes whose children are
 // SFANode / PCANode / WhiteningNode / GeneralExpansionNode / iGSFANode (reference call sites
 // FaceDetectUpdated.py:699, face_analysis.py:1064,1257).
 //
 // Data layout in HBM ("TILED", hgsfa.h): activations of every layer are kept window-minor,
-//   X[tile][feature][128 windows], so that one warp reading one feature of one tile moves 512
-// contiguous bytes and the receptive-field gather of a Switchboard is a *feature-index* indirection
-// that is uniform across the warp -- the gather costs no extra memory traffic and is fused into the
-// operand fetch of the projection.
+//   X[tile][feature][128 windows], so the receptive-field gather of a Switchboard becomes a list of
+// contiguous byte ranges (feature runs) that TMA bulk copies fetch, and every warp-level access to one
+// feature of one tile is a single 512-byte line set.
 //
-// One layer operation = for every (node, window tile):
-//     x0 = X[gather[node]] - in_offset[node]                      (Switchboard + mean subtraction)
-//     for each pass p:   A_p = terms_p(x0, rows of earlier passes) (GeneralExpansion term table)
-//                        Y_p = A_p @ W_p[node] + b_p[node]         (SFA / PCA / iGSFA projection)
-//                        Y_p -> global output columns and/or shared-memory rows
-// Expanded features (A_p) only ever exist as 16-row chunks in shared memory; the slow-feature part of
-// an iGSFA node stays in shared memory between its two passes.
-//
-// Thread mapping: a CTA of 4 warps owns (node, TWC window tiles).  Lanes own 4 consecutive windows
-// (one float4) so all weight reads are warp-uniform shared-memory broadcasts; a thread accumulates a
-// 4 windows x NT outputs register tile with packed FFMA2 (fma.rn.f32x2), the only way to leave issue
-// slots free next to the FP32 pipe on sm_100 (tools/microbench.cu: 72 TFLOP/s either way, but FFMA
-// alone saturates the issue port).
+// Scheduling: layers with many nodes ("front" segment) run over chunks of front_chunk windows so that
+// their activations stay L2-resident between launches; the last layers, which have only a few nodes,
+// run once per back_chunk windows so that every launch still fills the 148 SMs.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
 #include "common.cuh"
+#include "layer.cuh"
 
 namespace hgsfa {
-
-constexpr int KC = 16;         // expansion rows per shared-memory chunk
-constexpr int TILE = HGSFA_TILE;
-constexpr int MAX_PASSES = 4;
-constexpr int THREADS = 128;
-
-enum TermOp { OP_ID = 0, OP_MUL = 1, OP_ABSPOW = 2, OP_SGNPOW = 3, OP_MUL3 = 4, OP_ABS = 5, OP_CLIP = 6 };
-enum { DST_GLOBAL = 1, DST_ROWS = 2 };
-
-struct Term { int32_t op, i, j; float p; };
-
-struct PassDev {
-  const Term* terms;
-  const float* W;      // [n_w][K][Npad]
-  const float* b;      // [n_w][Npad]
-  const int* n_valid;  // [n_nodes] columns written to global
-  const int* col_off;  // [n_nodes] first column (relative to the node's out_col)
-  int K, Npad, dst, row0, cfg;
-};
-
-struct OpDev {
-  int n_nodes, d_in, in_dim, out_dim, n_passes, shared, n_rows, twc;
-  float clip_lo, clip_hi;  // saturation applied to values stored to the output buffer
-  const int* gather;       // [n_nodes][d_in] feature index in the input buffer
-  const float* in_offset;  // [n_w][d_in]
-  const int* out_col;      // [n_nodes]
-  PassDev pass[MAX_PASSES];
-};
-
-// ------------------------------------------------------------------------------------------------
-// operand fetch
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 ld_tiled(const float* x, size_t idx4) {
-  return __ldg(reinterpret_cast<const float4*>(x) + idx4);
-}
-__device__ __forceinline__ float4 ld_tiled(const uint8_t* x, size_t idx4) {
-  uchar4 v = __ldg(reinterpret_cast<const uchar4*>(x) + idx4);
-  return make_float4(float(v.x), float(v.y), float(v.z), float(v.w));
-}
-
-__device__ __forceinline__ float abspow(float x, float p) {
-  // |x|^p, p > 0; lg2(0) = -inf -> ex2(-inf) = 0
-  return exp2f(p * __log2f(fabsf(x)));
-}
-
-template <typename IN_T>
-struct Fetch {
-  const OpDev& op;
-  const IN_T* xin;
-  const float* sR;  // [n_rows][twc][128]
-  const int* gather;
-  const float* offs;
-  int lane;
-
-  // value of source row i for window tile `tile` (global) / tile slot `slot` (shared rows)
-  __device__ __forceinline__ float4 operator()(int i, int64_t tile, int slot) const {
-    if (i < op.d_in) {
-      const int f = __ldg(gather + i);
-      const float o = __ldg(offs + i);
-      float4 v = ld_tiled(xin, (size_t(tile) * op.in_dim + f) * (TILE / 4) + lane);
-      v.x -= o; v.y -= o; v.z -= o; v.w -= o;
-      return v;
-    }
-    return reinterpret_cast<const float4*>(sR)[(size_t(i - op.d_in) * op.twc + slot) * (TILE / 4) + lane];
-  }
-};
-
-template <typename IN_T>
-__device__ __forceinline__ float4 eval_term(const Term t, const Fetch<IN_T>& src, int64_t tile, int slot) {
-  float4 a = src(t.i, tile, slot);
-  switch (t.op) {
-    case OP_ID:
-      return a;
-    case OP_MUL: {
-      float4 b = src(t.j, tile, slot);
-      return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
-    }
-    case OP_ABSPOW:
-      return make_float4(abspow(a.x, t.p), abspow(a.y, t.p), abspow(a.z, t.p), abspow(a.w, t.p));
-    case OP_SGNPOW:
-      return make_float4(copysignf(abspow(a.x, t.p), a.x), copysignf(abspow(a.y, t.p), a.y),
-                         copysignf(abspow(a.z, t.p), a.z), copysignf(abspow(a.w, t.p), a.w));
-    case OP_MUL3: {
-      float4 b = src(t.j, tile, slot);
-      float4 c = src(int(t.p), tile, slot);
-      return make_float4(a.x * b.x * c.x, a.y * b.y * c.y, a.z * b.z * c.z, a.w * b.w * c.w);
-    }
-    case OP_ABS:
-      return make_float4(fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w));
-    case OP_CLIP:
-      return make_float4(fminf(fmaxf(a.x, -t.p), t.p), fminf(fmaxf(a.y, -t.p), t.p),
-                         fminf(fmaxf(a.z, -t.p), t.p), fminf(fmaxf(a.w, -t.p), t.p));
-    default:
-      return make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// packed FP32 FMA:  (d.lo, d.hi) += (a, a) * (w.lo, w.hi)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a2, unsigned long long w2) {
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a2), "l"(w2));
-}
-__device__ __forceinline__ unsigned long long dup2(float a) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(a));
-  return r;
-}
-__device__ __forceinline__ float2 unpack2(unsigned long long v) {
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
-}
-
-__device__ __forceinline__ float4 clamp4(float4 v, float lo, float hi) {
-  return make_float4(fminf(fmaxf(v.x, lo), hi), fminf(fmaxf(v.y, lo), hi), fminf(fmaxf(v.z, lo), hi),
-                     fminf(fmaxf(v.w, lo), hi));
-}
-
-// ------------------------------------------------------------------------------------------------
-// one pass: A = terms(x0, rows);  Y = A @ W + b
-//   WM window tiles x WN column tiles of NT outputs are processed concurrently by the 4 warps.
-// ------------------------------------------------------------------------------------------------
-template <typename IN_T, int WM, int WN, int NT>
-__device__ __forceinline__ void run_pass(const OpDev& op, const PassDev& ps, const IN_T* __restrict__ xin,
-                                         float* __restrict__ xout, int64_t tile0, int64_t ntiles, int node,
-                                         float* sA, float* sW, float* sR) {
-  static_assert(WM * WN == THREADS / 32, "warp grid must cover the CTA");
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int wm = warp / WN, wn = warp % WN;
-  const int nw = op.shared ? 0 : node;
-  const float* Wg = ps.W + size_t(nw) * ps.K * ps.Npad;
-  const float* bg = ps.b + size_t(nw) * ps.Npad;
-  Fetch<IN_T> src{op, xin, sR, op.gather + size_t(node) * op.d_in, op.in_offset + size_t(nw) * op.d_in, lane};
-  const int n0 = wn * NT;                 // first output column of this warp
-  const bool col_active = n0 < ps.Npad;   // Npad is a multiple of NT
-  const int w_chunk4 = KC * ps.Npad / 4;
-
-  for (int tg = 0; tg < op.twc; tg += WM) {
-    unsigned long long acc[4][NT / 2];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int q = 0; q < NT / 2; ++q) acc[r][q] = 0ull;
-    const int64_t my_tile = tile0 + tg + wm;
-    const bool tile_active = (tg + wm) < op.twc && my_tile < ntiles;
-
-    for (int k0 = 0; k0 < ps.K; k0 += KC) {
-      __syncthreads();  // previous chunk fully consumed (and rows of the previous pass visible)
-      // ---- build the expansion chunk A[KC][WM][128] ----
-      for (int u = warp; u < KC * WM; u += THREADS / 32) {
-        const int row = u / WM, slot = u % WM;
-        const int64_t tile = tile0 + tg + slot;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((tg + slot) < op.twc && tile < ntiles) {
-          const Term t = ps.terms[k0 + row];
-          v = eval_term(t, src, tile, tg + slot);
-        }
-        reinterpret_cast<float4*>(sA)[(row * WM + slot) * (TILE / 4) + lane] = v;
-      }
-      // ---- stage the weight chunk W[k0:k0+KC][Npad] ----
-      {
-        const float4* Wg4 = reinterpret_cast<const float4*>(Wg + size_t(k0) * ps.Npad);
-        float4* sW4 = reinterpret_cast<float4*>(sW);
-        for (int idx = tid; idx < w_chunk4; idx += THREADS) sW4[idx] = __ldg(Wg4 + idx);
-      }
-      __syncthreads();
-      // ---- register-tile GEMM: 4 windows x NT outputs per thread ----
-      if (tile_active && col_active) {
-        const float4* a4 = reinterpret_cast<const float4*>(sA) + wm * (TILE / 4) + lane;
-        const float* wrow = sW + n0;
-#pragma unroll 4
-        for (int kc = 0; kc < KC; ++kc) {
-          const float4 a = a4[kc * WM * (TILE / 4)];
-          const unsigned long long ax = dup2(a.x), ay = dup2(a.y), az = dup2(a.z), aw = dup2(a.w);
-          const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(wrow + kc * ps.Npad);
-#pragma unroll
-          for (int q = 0; q < NT / 4; ++q) {
-            const ulonglong2 w = w2[q];
-            ffma2(acc[0][2 * q], ax, w.x); ffma2(acc[0][2 * q + 1], ax, w.y);
-            ffma2(acc[1][2 * q], ay, w.x); ffma2(acc[1][2 * q + 1], ay, w.y);
-            ffma2(acc[2][2 * q], az, w.x); ffma2(acc[2][2 * q + 1], az, w.y);
-            ffma2(acc[3][2 * q], aw, w.x); ffma2(acc[3][2 * q + 1], aw, w.y);
-          }
-        }
-      }
-    }
-
-    // ---- epilogue: bias, then global columns and/or shared rows ----
-    if (tile_active && col_active) {
-      const int nvalid = (ps.dst & DST_GLOBAL) ? __ldg(ps.n_valid + node) : 0;
-      const int col0 = (ps.dst & DST_GLOBAL) ? (__ldg(op.out_col + node) + __ldg(ps.col_off + node)) : 0;
-#pragma unroll
-      for (int q = 0; q < NT / 2; ++q) {
-        const float2 y0 = unpack2(acc[0][q]), y1 = unpack2(acc[1][q]);
-        const float2 y2 = unpack2(acc[2][q]), y3 = unpack2(acc[3][q]);
-        const int n = n0 + 2 * q;
-        const float b0 = __ldg(bg + n), b1 = __ldg(bg + n + 1);
-        const float4 v0 = make_float4(y0.x + b0, y1.x + b0, y2.x + b0, y3.x + b0);
-        const float4 v1 = make_float4(y0.y + b1, y1.y + b1, y2.y + b1, y3.y + b1);
-        if (ps.dst & DST_GLOBAL) {
-          float4* o = reinterpret_cast<float4*>(xout) + (size_t(my_tile) * op.out_dim + col0) * (TILE / 4) + lane;
-          if (n < nvalid) o[size_t(n) * (TILE / 4)] = clamp4(v0, op.clip_lo, op.clip_hi);
-          if (n + 1 < nvalid) o[size_t(n + 1) * (TILE / 4)] = clamp4(v1, op.clip_lo, op.clip_hi);
-        }
-        if (ps.dst & DST_ROWS) {
-          float4* r4 = reinterpret_cast<float4*>(sR);
-          r4[(size_t(ps.row0 + n) * op.twc + (tg + wm)) * (TILE / 4) + lane] = v0;
-          r4[(size_t(ps.row0 + n + 1) * op.twc + (tg + wm)) * (TILE / 4) + lane] = v1;
-        }
-      }
-    }
-  }
-}
-
-// NTMAX = 16 omits the 4 x 32 register tile (cfg 3) so that the common instantiation keeps a small
-// register footprint; ops whose widest pass has more than 64 output columns use NTMAX = 32.
-template <typename IN_T, int NTMAX>
-__global__ void __launch_bounds__(THREADS) layer_kernel(const OpDev op, const IN_T* __restrict__ xin,
-                                                        float* __restrict__ xout, int64_t ntiles, int npad_max) {
-  extern __shared__ __align__(16) float smem[];
-  float* sA = smem;                              // [KC][twc][128]
-  float* sW = sA + KC * op.twc * TILE;           // [KC][npad_max]
-  float* sR = sW + KC * npad_max;                // [n_rows][twc][128]
-  const int node = blockIdx.y;
-  const int64_t tile0 = int64_t(blockIdx.x) * op.twc;
-#pragma unroll 1
-  for (int p = 0; p < op.n_passes; ++p) {
-    const PassDev& ps = op.pass[p];
-    switch (ps.cfg) {
-      case 0: run_pass<IN_T, 4, 1, 16>(op, ps, xin, xout, tile0, ntiles, node, sA, sW, sR); break;
-      case 1: run_pass<IN_T, 2, 2, 16>(op, ps, xin, xout, tile0, ntiles, node, sA, sW, sR); break;
-      case 2: run_pass<IN_T, 1, 4, 16>(op, ps, xin, xout, tile0, ntiles, node, sA, sW, sR); break;
-      default:
-        if constexpr (NTMAX >= 32) run_pass<IN_T, 1, 4, 32>(op, ps, xin, xout, tile0, ntiles, node, sA, sW, sR);
-        break;
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // layout kernels: row-major <-> tiled
@@ -319,17 +71,38 @@ __global__ void __launch_bounds__(256) untile_kernel(const float* __restrict__ s
 // ------------------------------------------------------------------------------------------------
 // host side: plan
 // ------------------------------------------------------------------------------------------------
-struct PassHost {
-  int K, Npad, dst, row0, cfg, K_real, N_real;
-};
 struct OpHost {
-  OpDev dev;
-  PassHost pass[MAX_PASSES];
+  OpDev dev;             // pointers valid on the device; layout fields filled per launch
   int64_t alg_flops, exe_flops;
-  int npad_max;
-  bool wide;   // some pass uses the 4 x 32 register tile (cfg 3)
-  size_t smem_bytes;
+  bool wide;             // some pass uses a 24 / 32 column register tile
+  int scratch_floats;    // K-split scratch (floats)
+  size_t smem_bytes[2];  // dynamic shared memory for [f32 input, u8 input]
+  int nstages[2];
 };
+
+// shared-memory layout for input element size `el`; returns total bytes (0 if nothing fits)
+static size_t layout_op(OpDev& d, int scratch_floats, int el, int* nstages_out) {
+  const size_t raw = size_t(d.d_in) * TILE * el;                       // per tile slot
+  const size_t stage = (size_t(d.twc) * raw + size_t(d.param_floats) * 4 + 127) & ~size_t(127);
+  size_t off = 128;                                                     // mbarriers
+  d.sm_terms = (int)off;
+  off += (size_t(d.n_terms) * sizeof(Term16) + 127) & ~size_t(127);
+  d.sm_srows = (int)off;
+  off += (size_t(d.twc) * d.n_rows * TILE * 4 + 127) & ~size_t(127);
+  d.sm_scratch = (int)off;
+  off += (size_t(scratch_floats) * 4 + 127) & ~size_t(127);
+  d.sm_stage0 = (int)off;
+  d.sm_stage_bytes = (int)stage;
+  d.sm_raw_bytes = (int)raw;
+  const size_t limit = 227 * 1024;
+  int ns = (off + 2 * stage <= limit && d.npc > 1) ? 2 : 1;
+  // two stages only pay when they do not cost the second resident CTA
+  if (ns == 2 && off + 2 * stage > 113 * 1024 && off + stage <= 113 * 1024) ns = 1;
+  if (off + ns * stage > limit) return 0;
+  d.nstages = ns;
+  *nstages_out = ns;
+  return off + ns * stage;
+}
 
 }  // namespace hgsfa
 
@@ -337,13 +110,13 @@ using namespace hgsfa;
 
 struct hgsfa_plan_s {
   int device = 0;
-  cudaStream_t stream = nullptr;     // compute stream owned by the plan
+  cudaStream_t stream = nullptr;     // compute stream owned by the plan (host entry point)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   int64_t input_dim = 0, output_dim = 0;
   std::vector<OpHost> ops;
-  DevBuf params;                     // all plan arrays in one allocation
+  DevBuf params;                     // the whole blob: every plan array is an offset into it
   DevBuf tin, front[2], mid, back[2], stage_x[2], stage_y[2];
   int64_t front_chunk = 16384, back_chunk = 262144;
   int split = 0;                     // ops [0, split) run per front chunk, [split, n) per back chunk
@@ -367,24 +140,32 @@ struct Cursor {
   }
 };
 
-const int CFG_WM[4] = {4, 2, 1, 1};
-const int CFG_NT[4] = {16, 16, 16, 32};
-const int CFG_WN[4] = {1, 2, 4, 4};
-
 template <typename IN_T>
-int launch_layer(hgsfa_plan_s* pl, const OpHost& op, const void* xin, float* xout, int64_t ntiles,
-                 cudaStream_t st) {
+int launch_layer(hgsfa_plan_s* pl, OpHost& op, const void* xin, float* xout, int64_t ntiles, cudaStream_t st) {
   if (ntiles <= 0) return 0;
-  dim3 grid((unsigned)ceil_div(ntiles, op.dev.twc), (unsigned)op.dev.n_nodes);
+  const int v = sizeof(IN_T) == 1 ? 1 : 0;
+  OpDev d = op.dev;
+  int ns = 1;
+  layout_op(d, op.scratch_floats, (int)sizeof(IN_T), &ns);
+  dim3 grid((unsigned)ceil_div(ntiles, d.twc), (unsigned)ceil_div(d.n_nodes, d.npc));
   if (op.wide)
-    layer_kernel<IN_T, 32><<<grid, THREADS, op.smem_bytes, st>>>(op.dev, static_cast<const IN_T*>(xin), xout, ntiles,
-                                                                op.npad_max);
+    layer_kernel<IN_T, 32><<<grid, THREADS, op.smem_bytes[v], st>>>(d, static_cast<const IN_T*>(xin), xout, ntiles);
   else
-    layer_kernel<IN_T, 16><<<grid, THREADS, op.smem_bytes, st>>>(op.dev, static_cast<const IN_T*>(xin), xout, ntiles,
-                                                                op.npad_max);
+    layer_kernel<IN_T, 16><<<grid, THREADS, op.smem_bytes[v], st>>>(d, static_cast<const IN_T*>(xin), xout, ntiles);
   pl->launches++;
   HG_CUDA(cudaGetLastError());
   return 0;
+}
+
+int plan_fail(hgsfa_plan_s* pl, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  pl->params.release();
+  delete pl;
+  return fail("hgsfa_plan_create: %s", buf);
 }
 
 }  // namespace
@@ -399,24 +180,19 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
   HG_CHECK(guard.ok, "hgsfa_plan_create: cannot select device %d", device);
 
   const uint8_t* base = static_cast<const uint8_t*>(blob);
-  HG_CHECK(std::memcmp(base, "HGSFAPL1", 8) == 0, "hgsfa_plan_create: bad magic (not a plan blob)");
+  HG_CHECK(std::memcmp(base, "HGSFAPL2", 8) == 0, "hgsfa_plan_create: bad magic (not a version-2 plan blob)");
   const int64_t* hdr = reinterpret_cast<const int64_t*>(base + 8);
   auto pl = new hgsfa_plan_s();
   pl->device = device;
   pl->input_dim = hdr[0];
   pl->output_dim = hdr[1];
   const int64_t n_ops = hdr[2];
-  if (n_ops <= 0 || n_ops > 4096 || pl->input_dim <= 0 || pl->output_dim <= 0) {
-    delete pl;
-    return fail("hgsfa_plan_create: implausible header (n_ops=%lld in=%lld out=%lld)", (long long)n_ops,
-                (long long)hdr[0], (long long)hdr[1]);
-  }
-  // the device copy of the blob: array pointers below are offsets into it
+  if (n_ops <= 0 || n_ops > 4096 || pl->input_dim <= 0 || pl->output_dim <= 0)
+    return plan_fail(pl, "implausible header (n_ops=%lld in=%lld out=%lld)", (long long)n_ops, (long long)hdr[0],
+                     (long long)hdr[1]);
   if (pl->params.reserve(nbytes)) { delete pl; return 1; }
-  if (cudaMemcpy(pl->params.p, blob, nbytes, cudaMemcpyHostToDevice) != cudaSuccess) {
-    pl->params.release(); delete pl;
-    return fail("hgsfa_plan_create: parameter upload failed");
-  }
+  if (cudaMemcpy(pl->params.p, blob, nbytes, cudaMemcpyHostToDevice) != cudaSuccess)
+    return plan_fail(pl, "parameter upload failed");
   const uint8_t* dbase = static_cast<const uint8_t*>(pl->params.p);
   auto dev_ptr = [&](const void* host) { return dbase + (static_cast<const uint8_t*>(host) - base); };
 
@@ -430,117 +206,108 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
     d.n_nodes = (int)oh[0]; d.d_in = (int)oh[1]; d.in_dim = (int)oh[2]; d.out_dim = (int)oh[3];
     d.n_passes = (int)oh[4]; d.shared = (int)oh[5]; d.n_rows = (int)oh[6]; d.twc = (int)oh[7];
     op.alg_flops = oh[8]; op.exe_flops = oh[9];
+    d.npc = (int)oh[10]; d.n_runs = (int)oh[11];
     {
       double clip[2];
       std::memcpy(clip, oh + 12, sizeof(clip));
       d.clip_lo = float(clip[0]); d.clip_hi = float(clip[1]);
     }
-    bool sane = d.n_nodes > 0 && d.n_nodes <= 65535 && d.d_in > 0 && d.in_dim == cur_dim && d.out_dim > 0 &&
-                d.n_passes >= 1 && d.n_passes <= MAX_PASSES && (d.twc == 1 || d.twc == 2 || d.twc == 4) &&
-                d.n_rows >= 0;
-    if (!sane) {
-      pl->params.release(); delete pl;
-      return fail("hgsfa_plan_create: op %lld has an inconsistent header (nodes=%d d_in=%d in_dim=%d expected %lld)",
-                  (long long)o, d.n_nodes, d.d_in, d.in_dim, (long long)cur_dim);
-    }
+    d.param_floats = (int)oh[14]; d.n_terms = (int)oh[15];
+    const bool sane = d.n_nodes > 0 && d.n_nodes <= 65535 * 64 && d.d_in > 0 && d.d_in < 32768 && d.in_dim == cur_dim &&
+                      d.out_dim > 0 && d.n_passes >= 1 && d.n_passes <= MAX_PASSES &&
+                      (d.twc == 1 || d.twc == 2 || d.twc == 4 || d.twc == 8) && d.n_rows >= 0 && d.npc >= 1 &&
+                      d.n_runs >= 1 && d.n_runs <= d.d_in && d.param_floats > 0 && d.param_floats % 4 == 0 &&
+                      d.n_terms > 0;
+    if (!sane)
+      return plan_fail(pl, "op %lld has an inconsistent header (nodes=%d d_in=%d in_dim=%d expected %lld twc=%d)",
+                       (long long)o, d.n_nodes, d.d_in, d.in_dim, (long long)cur_dim, d.twc);
     const int n_w = d.shared ? 1 : d.n_nodes;
-    const int32_t* gather = cur.take<int32_t>(size_t(d.n_nodes) * d.d_in);
-    const float* in_off = cur.take<float>(size_t(n_w) * d.d_in);
+    const Run* runs = cur.take<Run>(size_t(d.n_nodes) * d.n_runs);
     const int32_t* out_col = cur.take<int32_t>(d.n_nodes);
+    const float* params = cur.take<float>(size_t(n_w) * d.param_floats);
+    const Term16* terms = cur.take<Term16>(d.n_terms);
     if (!cur.ok) break;
-    for (size_t g = 0; g < size_t(d.n_nodes) * d.d_in; ++g)
-      if (gather[g] < 0 || gather[g] >= d.in_dim) {
-        pl->params.release(); delete pl;
-        return fail("hgsfa_plan_create: op %lld gather index %d outside [0,%d)", (long long)o, gather[g], d.in_dim);
+    for (int nd = 0; nd < d.n_nodes; ++nd) {   // the runs of a node must tile its d_in rows inside the input buffer
+      int covered = 0;
+      for (int r = 0; r < d.n_runs; ++r) {
+        const Run& rn = runs[size_t(nd) * d.n_runs + r];
+        if (rn.len == 0) continue;
+        if (rn.len < 0 || rn.i0 != covered || rn.f0 < 0 || rn.f0 + rn.len > d.in_dim)
+          return plan_fail(pl, "op %lld node %d: bad gather run (i0=%d f0=%d len=%d)", (long long)o, nd, rn.i0, rn.f0, rn.len);
+        covered += rn.len;
       }
-    d.gather = reinterpret_cast<const int*>(dev_ptr(gather));
-    d.in_offset = reinterpret_cast<const float*>(dev_ptr(in_off));
+      if (covered != d.d_in) return plan_fail(pl, "op %lld node %d: gather runs cover %d of %d rows", (long long)o, nd, covered, d.d_in);
+    }
+    d.runs = reinterpret_cast<const Run*>(dev_ptr(runs));
     d.out_col = reinterpret_cast<const int*>(dev_ptr(out_col));
-    op.npad_max = 0;
-    int max_wm = 1;
+    d.params = reinterpret_cast<const float*>(dev_ptr(params));
+    d.terms = reinterpret_cast<const Term16*>(dev_ptr(terms));
+    const int n_src = d.d_in + d.n_rows;
+    for (int k = 0; k < d.n_terms; ++k)
+      if (terms[k].i < 0 || terms[k].i >= n_src || terms[k].j < 0 || terms[k].j >= n_src || terms[k].k < 0 || terms[k].k >= n_src)
+        return plan_fail(pl, "op %lld term %d references a row outside [0, %d)", (long long)o, k, n_src);
+    op.scratch_floats = 0;
     for (int p = 0; p < d.n_passes && cur.ok; ++p) {
-      const int64_t* ph = cur.take<int64_t>(8);
+      const int64_t* ph = cur.take<int64_t>(16);
       if (!ph) break;
-      PassHost& hp = op.pass[p];
-      hp.K = (int)ph[0]; hp.Npad = (int)ph[1]; hp.dst = (int)ph[2]; hp.row0 = (int)ph[3]; hp.cfg = (int)ph[4];
-      hp.K_real = (int)ph[5]; hp.N_real = (int)ph[6];
-      bool psane = hp.K > 0 && hp.K % KC == 0 && hp.cfg >= 0 && hp.cfg <= 3 && hp.Npad > 0 &&
-                   hp.Npad % CFG_NT[hp.cfg] == 0 && hp.Npad <= CFG_NT[hp.cfg] * CFG_WN[hp.cfg] &&
-                   (hp.dst & (DST_GLOBAL | DST_ROWS)) && hp.row0 >= 0 &&
-                   (!(hp.dst & DST_ROWS) || hp.row0 + hp.Npad <= d.n_rows);
-      if (!psane) {
-        pl->params.release(); delete pl;
-        return fail("hgsfa_plan_create: op %lld pass %d inconsistent (K=%d Npad=%d cfg=%d dst=%d row0=%d rows=%d)",
-                    (long long)o, p, hp.K, hp.Npad, hp.cfg, hp.dst, hp.row0, d.n_rows);
-      }
-      const Term* terms = cur.take<Term>(hp.K);
-      const float* W = cur.take<float>(size_t(n_w) * hp.K * hp.Npad);
-      const float* b = cur.take<float>(size_t(n_w) * hp.Npad);
+      PassDev& dp = d.pass[p];
+      dp.K = (int)ph[0]; dp.Npad = (int)ph[1]; dp.NT = (int)ph[2]; dp.NTL = (int)ph[3]; dp.KS = (int)ph[4];
+      dp.TW = (int)ph[5]; dp.dst = (int)ph[6]; dp.row0 = (int)ph[7]; dp.w_off = (int)ph[8]; dp.b_off = (int)ph[9];
+      dp.term_off = (int)ph[10]; dp.n_seg = (int)ph[11];
+      const bool psane =
+          dp.K > 0 && (dp.NT == 8 || dp.NT == 16 || dp.NT == 24 || dp.NT == 32) && dp.NTL >= 1 && dp.KS >= 1 &&
+          dp.TW >= 1 && dp.NTL * dp.KS * dp.TW == WARPS && dp.Npad == dp.NT * dp.NTL && d.twc % dp.TW == 0 &&
+          (dp.KS & (dp.KS - 1)) == 0 && (dp.dst & (DST_GLOBAL | DST_ROWS)) && dp.row0 >= 0 &&
+          (!(dp.dst & DST_ROWS) || dp.row0 + dp.Npad <= d.n_rows) && dp.w_off >= 0 && dp.w_off % 4 == 0 && dp.b_off >= 0 &&
+          dp.w_off + dp.K * dp.Npad <= d.param_floats && dp.b_off + dp.Npad <= d.param_floats && dp.term_off >= 0 &&
+          dp.term_off + dp.K <= d.n_terms && dp.n_seg >= 1;
+      if (!psane)
+        return plan_fail(pl, "op %lld pass %d inconsistent (K=%d Npad=%d NT=%d NTL=%d KS=%d TW=%d dst=%d row0=%d)",
+                         (long long)o, p, dp.K, dp.Npad, dp.NT, dp.NTL, dp.KS, dp.TW, dp.dst, dp.row0);
+      const Seg* segs = cur.take<Seg>(dp.n_seg);
       const int32_t* n_valid = cur.take<int32_t>(d.n_nodes);
       const int32_t* col_off = cur.take<int32_t>(d.n_nodes);
       if (!cur.ok) break;
-      const int n_src = d.d_in + d.n_rows;
-      for (int k = 0; k < hp.K; ++k) {
-        const Term& t = terms[k];
-        bool tok = t.op >= 0 && t.op <= OP_CLIP && t.i >= 0 && t.i < n_src;
-        if (t.op == OP_MUL || t.op == OP_MUL3) tok = tok && t.j >= 0 && t.j < n_src;
-        if (t.op == OP_MUL3) tok = tok && int(t.p) >= 0 && int(t.p) < n_src;
-        if (!tok) {
-          pl->params.release(); delete pl;
-          return fail("hgsfa_plan_create: op %lld pass %d term %d invalid (op=%d i=%d j=%d)", (long long)o, p, k,
-                      t.op, t.i, t.j);
-        }
+      int kcov = 0;
+      for (int sgi = 0; sgi < dp.n_seg; ++sgi) {
+        if (segs[sgi].op < 0 || segs[sgi].op > OP_CLIP || segs[sgi].k0 != kcov || segs[sgi].k1 < segs[sgi].k0)
+          return plan_fail(pl, "op %lld pass %d: bad term segment %d", (long long)o, p, sgi);
+        kcov = segs[sgi].k1;
       }
+      if (kcov != dp.K) return plan_fail(pl, "op %lld pass %d: segments cover %d of %d terms", (long long)o, p, kcov, dp.K);
       for (int nd = 0; nd < d.n_nodes; ++nd)
-        if ((hp.dst & DST_GLOBAL) &&
-            (n_valid[nd] < 0 || n_valid[nd] > hp.Npad || out_col[nd] + col_off[nd] < 0 ||
-             out_col[nd] + col_off[nd] + n_valid[nd] > d.out_dim)) {
-          pl->params.release(); delete pl;
-          return fail("hgsfa_plan_create: op %lld pass %d node %d writes outside the output buffer", (long long)o, p, nd);
-        }
-      PassDev& dp = d.pass[p];
-      dp.terms = reinterpret_cast<const Term*>(dev_ptr(terms));
-      dp.W = reinterpret_cast<const float*>(dev_ptr(W));
-      dp.b = reinterpret_cast<const float*>(dev_ptr(b));
+        if ((dp.dst & DST_GLOBAL) && (n_valid[nd] < 0 || n_valid[nd] > dp.Npad || out_col[nd] + col_off[nd] < 0 ||
+                                      out_col[nd] + col_off[nd] + n_valid[nd] > d.out_dim))
+          return plan_fail(pl, "op %lld pass %d node %d writes outside the output buffer", (long long)o, p, nd);
+      dp.segs = reinterpret_cast<const Seg*>(dev_ptr(segs));
       dp.n_valid = reinterpret_cast<const int*>(dev_ptr(n_valid));
       dp.col_off = reinterpret_cast<const int*>(dev_ptr(col_off));
-      dp.K = hp.K; dp.Npad = hp.Npad; dp.dst = hp.dst; dp.row0 = hp.row0; dp.cfg = hp.cfg;
-      if (hp.Npad > op.npad_max) op.npad_max = hp.Npad;
-      if (CFG_WM[hp.cfg] > max_wm) max_wm = CFG_WM[hp.cfg];
-      if (hp.cfg == 3) op.wide = true;
+      if (dp.NT > 16) op.wide = true;
+      if (dp.KS > 1) op.scratch_floats = std::max(op.scratch_floats, (WARPS / 2) * dp.NT * TILE);
     }
     if (!cur.ok) break;
-    if (d.twc < max_wm) {
-      pl->params.release(); delete pl;
-      return fail("hgsfa_plan_create: op %lld twc=%d smaller than a pass's tile group %d", (long long)o, d.twc, max_wm);
+    for (int v = 0; v < 2; ++v) {
+      OpDev tmp = d;
+      op.smem_bytes[v] = layout_op(tmp, op.scratch_floats, v ? 1 : 4, &op.nstages[v]);
     }
-    op.smem_bytes = sizeof(float) * (size_t(KC) * d.twc * TILE + size_t(KC) * op.npad_max +
-                                     size_t(d.n_rows) * d.twc * TILE);
-    if (op.smem_bytes > 227 * 1024) {
-      pl->params.release(); delete pl;
-      return fail("hgsfa_plan_create: op %lld needs %zu bytes of shared memory (> 227 KB)", (long long)o, op.smem_bytes);
-    }
+    if (op.smem_bytes[0] == 0)
+      return plan_fail(pl, "op %lld does not fit in 227 KB of shared memory (d_in=%d twc=%d)", (long long)o, d.d_in, d.twc);
     cur_dim = d.out_dim;
     pl->ops.push_back(op);
   }
-  if (!cur.ok || (int64_t)pl->ops.size() != n_ops || cur_dim != pl->output_dim) {
-    pl->params.release(); delete pl;
-    return fail("hgsfa_plan_create: truncated or inconsistent blob (%zu of %lld ops parsed, final dim %lld vs %lld)",
-                pl->ops.size(), (long long)n_ops, (long long)cur_dim, (long long)hdr[1]);
-  }
+  if (!cur.ok || (int64_t)pl->ops.size() != n_ops || cur_dim != pl->output_dim)
+    return plan_fail(pl, "truncated or inconsistent blob (%zu of %lld ops parsed, final dim %lld vs %lld)", pl->ops.size(),
+                     (long long)n_ops, (long long)cur_dim, (long long)hdr[1]);
   size_t max_smem = 0;
-  for (auto& op : pl->ops) max_smem = op.smem_bytes > max_smem ? op.smem_bytes : max_smem;
+  for (auto& op : pl->ops) max_smem = std::max(max_smem, std::max(op.smem_bytes[0], op.smem_bytes[1]));
   cudaError_t es[4] = {
       cudaFuncSetAttribute(layer_kernel<uint8_t, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
       cudaFuncSetAttribute(layer_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
       cudaFuncSetAttribute(layer_kernel<uint8_t, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
       cudaFuncSetAttribute(layer_kernel<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem)};
   for (cudaError_t e : es)
-    if (e != cudaSuccess) {
-      pl->params.release(); delete pl;
-      return fail("hgsfa_plan_create: cannot reserve %zu bytes of dynamic shared memory: %s", max_smem,
-                  cudaGetErrorString(e));
-    }
+    if (e != cudaSuccess)
+      return plan_fail(pl, "cannot reserve %zu bytes of dynamic shared memory: %s", max_smem, cudaGetErrorString(e));
   // back segment = trailing ops with few nodes: they need many windows per launch to fill 148 SMs
   pl->split = (int)pl->ops.size();
   while (pl->split > 0 && pl->ops[pl->split - 1].dev.n_nodes <= 8) pl->split--;
@@ -648,7 +415,7 @@ int run_ops(hgsfa_plan_s* pl, int o0, int o1, const void* xin, bool xin_u8, floa
   const void* cur = xin;
   bool cur_u8 = xin_u8;
   for (int o = o0; o < o1; ++o) {
-    const OpHost& op = pl->ops[o];
+    OpHost& op = pl->ops[o];
     float* dst = (o == o1 - 1) ? final_out : static_cast<float*>(pp[(o - o0) & 1].p);
     int rc = cur_u8 ? launch_layer<uint8_t>(pl, op, cur, dst, ntiles, st) : launch_layer<float>(pl, op, cur, dst, ntiles, st);
     if (rc) return rc;
@@ -675,7 +442,9 @@ extern "C" int hgsfa_plan_execute_device(hgsfa_plan_t pl, const void* d_x, int x
   if (n == 0) return 0;
   HG_CHECK(d_x && d_y, "hgsfa_plan_execute_device: null buffer");
   DeviceGuard guard(pl->device);
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : pl->stream;
+  // plain CUDA semantics: NULL is the (legacy) default stream, so callers that time or order work
+  // on stream 0 (e.g. torch's default stream) see these launches in that stream
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   const int n_ops = (int)pl->ops.size();
   const int split = pl->split;

@@ -195,7 +195,7 @@ extern "C" int hgsfa_gauss_regress_device(hgsfa_gauss_t h, const void* d_x, int 
   if (n == 0) return 0;
   HG_CHECK(d_x, "hgsfa_gauss_regress: null x");
   DeviceGuard guard(h->device);
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);  // NULL = default stream (CUDA semantics)
   if (x_dtype == HGSFA_F32)
     return launch_gauss<float>(h, static_cast<const float*>(d_x), n, ld, d_avg_labels, d_value, d_std, d_winner, d_probs, st);
   return launch_gauss<double>(h, static_cast<const double*>(d_x), n, ld, d_avg_labels, d_value, d_std, d_winner, d_probs, st);

@@ -1,0 +1,400 @@
+// Fused HiGSFA layer kernel, version 2 (sm_100a): TMA bulk loads + in-register expansion + FFMA2.
+//
+// One launch = one layer operation of the plan (csrc/flow.cu):  for every (node, tile of 128 windows)
+//     x0 = X[gather[node]] - x_mean[node]                     Switchboard gather + mean subtraction
+//     per pass p:  A = terms_p(x0, S)  (never materialised)   GeneralExpansion term table
+//                  Y = A @ W_p[node] + b_p[node]              SFA / PCA / iGSFA projection
+//                  Y -> output columns and/or shared rows S   (slow features feed the 2nd iGSFA pass)
+//
+// Design (what changed against v1 and why, profiles/README_r01.md):
+//  * the receptive field of a node is a handful of *contiguous feature runs* of the window-minor
+//    activation layout [tile][feature][128 windows]; each run is fetched with ONE cp.async.bulk
+//    (TMA bulk copy) into shared memory, completion signalled on an mbarrier.  The node's parameters
+//    (x_mean, b, W of every pass) are one more bulk copy.  No thread ever waits on a dependent global
+//    load inside the contraction loops (v1: long_scoreboard was the top stall).
+//  * loads of node i+1 are issued before node i is computed (two shared-memory stages) when they fit.
+//  * expansion terms are evaluated in registers by the warp that consumes them: a lane owns 4
+//    consecutive windows, reads x0 rows as one LDS.128, applies |x|^p / products, and feeds the
+//    result straight into packed FP32 FMAs (fma.rn.f32x2) against weight rows that are warp-uniform
+//    LDS.128 broadcasts.  Expanded features never touch shared or global memory.
+//  * warps are independent inside a pass: a warp owns (tile slot, column tile of NT outputs, K-split
+//    part) and runs sync-free over its rows; K-split partial sums meet once per pass in shared memory.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "hgsfa.h"
+
+namespace hgsfa {
+
+constexpr int TILE = HGSFA_TILE;   // windows per tile
+constexpr int MAX_PASSES = 4;
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+
+enum TermOp { OP_ID = 0, OP_MUL = 1, OP_ABSPOW = 2, OP_SGNPOW = 3, OP_MUL3 = 4, OP_ABS = 5, OP_CLIP = 6 };
+enum { DST_GLOBAL = 1, DST_ROWS = 2 };
+
+struct Term16 { int16_t i, j, k, pad; };        // source rows of one expansion term
+struct Seg { int32_t op, k0, k1; float p; };    // run of terms [k0, k1) sharing one op (and exponent)
+struct Run { int32_t i0, f0, len, pad; };       // rows [i0, i0+len) of x0 = features [f0, f0+len) of the input
+
+struct PassDev {
+  int K, Npad, NT, NTL, KS, TW;   // contraction size, padded columns, columns per warp, column tiles, K-split, tile slots per round
+  int dst, row0;                  // destination flags, first shared row
+  int w_off, b_off;               // float offsets of W[K][Npad] and b[Npad] inside the node parameter block
+  int term_off, n_seg;
+  const Seg* segs;
+  const int* n_valid;             // [n_nodes] columns written to the output buffer
+  const int* col_off;             // [n_nodes] first column relative to the node's out_col
+};
+
+struct OpDev {
+  int n_nodes, d_in, in_dim, out_dim, n_passes, shared, n_rows, twc;
+  int npc, n_runs, nstages, param_floats, n_terms;
+  float clip_lo, clip_hi;
+  const Run* runs;        // [n_nodes][n_runs]
+  const int* out_col;     // [n_nodes]
+  const float* params;    // [n_w][param_floats]: x_mean[d_in (pad 4)] | per pass b[Npad], W[K][Npad]
+  const Term16* terms;    // [n_terms]
+  // shared-memory layout (bytes), filled by the host for the input element size in use
+  int sm_terms, sm_stage0, sm_stage_bytes, sm_raw_bytes, sm_srows, sm_scratch;
+  PassDev pass[MAX_PASSES];
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (TMA), packed FMA
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a2, unsigned long long w2) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a2), "l"(w2));
+}
+__device__ __forceinline__ unsigned long long dup2(float a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ unsigned long long pack2(float2 v) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+__device__ __forceinline__ float abspow(float x, float p) {
+  return exp2f(p * __log2f(fabsf(x)));   // |x|^p, p > 0: lg2(0) = -inf -> ex2(-inf) = 0
+}
+__device__ __forceinline__ float4 clamp4(float4 v, float lo, float hi) {
+  return make_float4(fminf(fmaxf(v.x, lo), hi), fminf(fmaxf(v.y, lo), hi), fminf(fmaxf(v.z, lo), hi),
+                     fminf(fmaxf(v.w, lo), hi));
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand fetch: row i of the node's source space for this lane's 4 windows
+//   i <  d_in : receptive-field row (IN_T in the staged buffer), minus x_mean[i]
+//   i >= d_in : shared row written by an earlier pass (float)
+// ------------------------------------------------------------------------------------------------
+template <typename IN_T>
+struct Rows {
+  const IN_T* raw;      // [d_in][128] of this tile slot
+  const float* srow;    // [n_rows][128] of this tile slot
+  const float* mean;    // [d_in] in the staged parameter block
+  int d_in, lane;
+  __device__ __forceinline__ float4 operator()(int i) const {
+    if (i < d_in) {
+      float4 v;
+      if (sizeof(IN_T) == 1) {
+        const uchar4 u = reinterpret_cast<const uchar4*>(raw)[i * (TILE / 4) + lane];
+        v = make_float4(float(u.x), float(u.y), float(u.z), float(u.w));
+      } else {
+        v = reinterpret_cast<const float4*>(raw)[i * (TILE / 4) + lane];
+      }
+      const float m = mean[i];
+      v.x -= m; v.y -= m; v.z -= m; v.w -= m;
+      return v;
+    }
+    return reinterpret_cast<const float4*>(srow)[(i - d_in) * (TILE / 4) + lane];
+  }
+};
+
+template <int NT>
+__device__ __forceinline__ void fma_row(unsigned long long (&acc)[4][NT / 2], const float4 a, const float* wrow) {
+  const unsigned long long ax = dup2(a.x), ay = dup2(a.y), az = dup2(a.z), aw = dup2(a.w);
+  const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(wrow);
+#pragma unroll
+  for (int q = 0; q < NT / 4; ++q) {
+    const ulonglong2 w = w2[q];
+    ffma2(acc[0][2 * q], ax, w.x); ffma2(acc[0][2 * q + 1], ax, w.y);
+    ffma2(acc[1][2 * q], ay, w.x); ffma2(acc[1][2 * q + 1], ay, w.y);
+    ffma2(acc[2][2 * q], az, w.x); ffma2(acc[2][2 * q + 1], az, w.y);
+    ffma2(acc[3][2 * q], aw, w.x); ffma2(acc[3][2 * q + 1], aw, w.y);
+  }
+}
+
+// bias + saturation + store of 4 windows x 1 column
+struct Epilogue {
+  const OpDev& op;
+  const PassDev& ps;
+  const float* bias;   // staged
+  float* xout;
+  float* srow;         // [n_rows][128] of the tile slot
+  int64_t tile;
+  int nvalid, col0, lane;
+  __device__ __forceinline__ void operator()(int n, float4 v) const {
+    const float b = bias[n];
+    v.x += b; v.y += b; v.z += b; v.w += b;
+    if ((ps.dst & DST_GLOBAL) && n < nvalid)
+      reinterpret_cast<float4*>(xout)[(size_t(tile) * op.out_dim + col0 + n) * (TILE / 4) + lane] =
+          clamp4(v, op.clip_lo, op.clip_hi);
+    if (ps.dst & DST_ROWS) reinterpret_cast<float4*>(srow)[(ps.row0 + n) * (TILE / 4) + lane] = v;
+  }
+};
+
+template <typename IN_T, int NT>
+__device__ __forceinline__ void run_pass(const OpDev& op, const PassDev& ps, int node, int64_t tile0, int64_t ntiles,
+                                         const uint8_t* stage, uint8_t* smem, float* __restrict__ xout) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = warp % ps.KS;
+  const int nt = (warp / ps.KS) % ps.NTL;
+  const int tw = warp / (ps.KS * ps.NTL);
+  const int n0 = nt * NT;
+  const float* params = reinterpret_cast<const float*>(stage + size_t(op.twc) * op.sm_raw_bytes);
+  const float* W = params + ps.w_off + n0;
+  const Term16* terms = reinterpret_cast<const Term16*>(smem + op.sm_terms) + ps.term_off;
+  float* scratch = reinterpret_cast<float*>(smem + op.sm_scratch);
+  const int nvalid = (ps.dst & DST_GLOBAL) ? __ldg(ps.n_valid + node) : 0;
+  const int col0 = (ps.dst & DST_GLOBAL) ? (__ldg(op.out_col + node) + __ldg(ps.col_off + node)) : 0;
+  const int Npad = ps.Npad, KS = ps.KS;
+
+  for (int r0 = 0; r0 < op.twc; r0 += ps.TW) {
+    const int slot = r0 + tw;
+    const int64_t tile = tile0 + slot;
+    const bool active = tw < ps.TW && slot < op.twc && tile < ntiles && n0 < Npad;
+    float* srow = reinterpret_cast<float*>(smem + op.sm_srows) + size_t(slot) * op.n_rows * TILE;
+    unsigned long long acc[4][NT / 2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < NT / 2; ++q) acc[r][q] = 0ull;
+
+    if (active) {
+      Rows<IN_T> rows{reinterpret_cast<const IN_T*>(stage + size_t(slot) * op.sm_raw_bytes), srow, params, op.d_in, lane};
+      for (int s = 0; s < ps.n_seg; ++s) {
+        const Seg sg = ps.segs[s];
+        const int kb = sg.k0 + ks;
+        switch (sg.op) {
+          case OP_ID:
+#pragma unroll 2
+            for (int k = kb; k < sg.k1; k += KS) fma_row<NT>(acc, rows(terms[k].i), W + k * Npad);
+            break;
+          case OP_MUL:
+#pragma unroll 2
+            for (int k = kb; k < sg.k1; k += KS) {
+              const Term16 t = terms[k];
+              const float4 a = rows(t.i), b = rows(t.j);
+              fma_row<NT>(acc, make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w), W + k * Npad);
+            }
+            break;
+          case OP_ABSPOW:
+#pragma unroll 2
+            for (int k = kb; k < sg.k1; k += KS) {
+              const float4 a = rows(terms[k].i);
+              fma_row<NT>(acc, make_float4(abspow(a.x, sg.p), abspow(a.y, sg.p), abspow(a.z, sg.p), abspow(a.w, sg.p)),
+                          W + k * Npad);
+            }
+            break;
+          case OP_SGNPOW:
+            for (int k = kb; k < sg.k1; k += KS) {
+              const float4 a = rows(terms[k].i);
+              fma_row<NT>(acc,
+                          make_float4(copysignf(abspow(a.x, sg.p), a.x), copysignf(abspow(a.y, sg.p), a.y),
+                                      copysignf(abspow(a.z, sg.p), a.z), copysignf(abspow(a.w, sg.p), a.w)),
+                          W + k * Npad);
+            }
+            break;
+          case OP_MUL3:
+            for (int k = kb; k < sg.k1; k += KS) {
+              const Term16 t = terms[k];
+              const float4 a = rows(t.i), b = rows(t.j), c = rows(t.k);
+              fma_row<NT>(acc, make_float4(a.x * b.x * c.x, a.y * b.y * c.y, a.z * b.z * c.z, a.w * b.w * c.w),
+                          W + k * Npad);
+            }
+            break;
+          case OP_ABS:
+            for (int k = kb; k < sg.k1; k += KS) {
+              const float4 a = rows(terms[k].i);
+              fma_row<NT>(acc, make_float4(fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w)), W + k * Npad);
+            }
+            break;
+          case OP_CLIP:
+            for (int k = kb; k < sg.k1; k += KS) {
+              const float4 a = rows(terms[k].i);
+              fma_row<NT>(acc, clamp4(a, -sg.p, sg.p), W + k * Npad);
+            }
+            break;
+          default:
+            break;
+        }
+      }
+    }
+
+    Epilogue epi{op, ps, params + ps.b_off, xout, srow, tile, nvalid, col0, lane};
+    if (KS == 1) {
+      if (active) {
+#pragma unroll
+        for (int q = 0; q < NT / 2; ++q) {
+          const float2 y0 = unpack2(acc[0][q]), y1 = unpack2(acc[1][q]), y2 = unpack2(acc[2][q]), y3 = unpack2(acc[3][q]);
+          epi(n0 + 2 * q, make_float4(y0.x, y1.x, y2.x, y3.x));
+          epi(n0 + 2 * q + 1, make_float4(y0.y, y1.y, y2.y, y3.y));
+        }
+      }
+    } else {
+      // K-split: pairwise tree over the KS warps of a group (consecutive warps).  In every round the
+      // upper half parks its partial sums in shared memory and the lower half adds them, so the
+      // scratch area holds at most WARPS / 2 register tiles.
+      const int grp_slot0 = (warp / KS) * (KS >> 1);   // first scratch slot of this warp's K-split group
+      for (int stride = KS >> 1; stride >= 1; stride >>= 1) {
+        // round: parts [stride, 2*stride) park their sums, parts [0, stride) add them
+        if (active && ks >= stride && ks < 2 * stride) {
+          float4* slot4 = reinterpret_cast<float4*>(scratch) + size_t(grp_slot0 + ks - stride) * NT * (TILE / 4) + lane;
+#pragma unroll
+          for (int q = 0; q < NT / 2; ++q) {
+            const float2 y0 = unpack2(acc[0][q]), y1 = unpack2(acc[1][q]), y2 = unpack2(acc[2][q]), y3 = unpack2(acc[3][q]);
+            slot4[(2 * q) * (TILE / 4)] = make_float4(y0.x, y1.x, y2.x, y3.x);
+            slot4[(2 * q + 1) * (TILE / 4)] = make_float4(y0.y, y1.y, y2.y, y3.y);
+          }
+        }
+        __syncthreads();
+        if (active && ks < stride) {
+          const float4* part = reinterpret_cast<const float4*>(scratch) + size_t(grp_slot0 + ks) * NT * (TILE / 4) + lane;
+#pragma unroll
+          for (int q = 0; q < NT / 2; ++q) {
+            const float4 u0 = part[(2 * q) * (TILE / 4)], u1 = part[(2 * q + 1) * (TILE / 4)];
+            float2 y0 = unpack2(acc[0][q]), y1 = unpack2(acc[1][q]), y2 = unpack2(acc[2][q]), y3 = unpack2(acc[3][q]);
+            y0.x += u0.x; y1.x += u0.y; y2.x += u0.z; y3.x += u0.w;
+            y0.y += u1.x; y1.y += u1.y; y2.y += u1.z; y3.y += u1.w;
+            acc[0][q] = pack2(y0); acc[1][q] = pack2(y1); acc[2][q] = pack2(y2); acc[3][q] = pack2(y3);
+          }
+        }
+        __syncthreads();   // scratch slots are reused by the next round / pass
+      }
+      if (active && ks == 0) {
+#pragma unroll
+        for (int q = 0; q < NT / 2; ++q) {
+          const float2 y0 = unpack2(acc[0][q]), y1 = unpack2(acc[1][q]), y2 = unpack2(acc[2][q]), y3 = unpack2(acc[3][q]);
+          epi(n0 + 2 * q, make_float4(y0.x, y1.x, y2.x, y3.x));
+          epi(n0 + 2 * q + 1, make_float4(y0.y, y1.y, y2.y, y3.y));
+        }
+      }
+    }
+  }
+}
+
+// NTMAX bounds the register tile compiled in: 16 (NT 8/16) keeps 2 CTAs per SM, 32 adds NT 24/32.
+template <typename IN_T, int NTMAX>
+__global__ void __launch_bounds__(THREADS, (NTMAX <= 16 ? 2 : 1))
+    layer_kernel(const OpDev op, const IN_T* __restrict__ xin, float* __restrict__ xout, int64_t ntiles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t tile0 = int64_t(blockIdx.x) * op.twc;
+  const int node_begin = blockIdx.y * op.npc;
+  const int node_end = min(op.n_nodes, node_begin + op.npc);
+  const int64_t tiles_left = ntiles - tile0;
+  const int valid_tiles = tiles_left < op.twc ? (int)tiles_left : op.twc;
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  {  // term table of all passes (shared by every node of the op)
+    const uint2* src = reinterpret_cast<const uint2*>(op.terms);
+    uint2* dst = reinterpret_cast<uint2*>(smem + op.sm_terms);
+    for (int i = tid; i < op.n_terms; i += THREADS) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  // producer: bulk copies of one node's receptive field (valid tile slots) + parameter block
+  auto issue = [&](int node, int s) {
+    uint8_t* stage = smem + op.sm_stage0 + size_t(s) * op.sm_stage_bytes;
+    const Run* runs = op.runs + size_t(node) * op.n_runs;
+    const int n_copies = 1 + valid_tiles * op.n_runs;
+    if (lane == 0) {
+      uint32_t bytes = uint32_t(op.param_floats) * 4u;
+      for (int r = 0; r < op.n_runs; ++r) bytes += uint32_t(valid_tiles) * uint32_t(runs[r].len) * TILE * sizeof(IN_T);
+      mbar_expect_tx(&full[s], bytes);
+    }
+    __syncwarp();
+    for (int c = lane; c < n_copies; c += 32) {
+      if (c == 0) {
+        const int nw = op.shared ? 0 : node;
+        bulk_g2s(stage + size_t(op.twc) * op.sm_raw_bytes, op.params + size_t(nw) * op.param_floats,
+                 uint32_t(op.param_floats) * 4u, &full[s]);
+      } else {
+        const int slot = (c - 1) / op.n_runs;
+        const Run r = runs[(c - 1) % op.n_runs];
+        if (r.len > 0)
+          bulk_g2s(stage + size_t(slot) * op.sm_raw_bytes + size_t(r.i0) * TILE * sizeof(IN_T),
+                   xin + (size_t(tile0 + slot) * op.in_dim + r.f0) * TILE, uint32_t(r.len) * TILE * sizeof(IN_T), &full[s]);
+      }
+    }
+  };
+
+  if (warp == 0 && node_begin < node_end) issue(node_begin, 0);
+  int it = 0;
+  for (int node = node_begin; node < node_end; ++node, ++it) {
+    const int s = (op.nstages == 2) ? (it & 1) : 0;
+    const uint32_t parity = (op.nstages == 2) ? ((it >> 1) & 1) : (it & 1);
+    if (op.nstages == 2 && warp == 0 && node + 1 < node_end) issue(node + 1, s ^ 1);
+    mbar_wait(&full[s], parity);
+    const uint8_t* stage = smem + op.sm_stage0 + size_t(s) * op.sm_stage_bytes;
+#pragma unroll 1
+    for (int p = 0; p < op.n_passes; ++p) {
+      const PassDev& ps = op.pass[p];
+      switch (ps.NT) {
+        case 8: run_pass<IN_T, 8>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+        case 16: run_pass<IN_T, 16>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+        case 24: if constexpr (NTMAX >= 32) run_pass<IN_T, 24>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+        case 32: if constexpr (NTMAX >= 32) run_pass<IN_T, 32>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+        default: break;
+      }
+      __syncthreads();   // shared rows of this pass visible; stage fully consumed after the last pass
+    }
+    if (op.nstages == 1 && warp == 0 && node + 1 < node_end) issue(node + 1, 0);
+  }
+}
+
+}  // namespace hgsfa

@@ -55,13 +55,15 @@ class GpuFlow(object):
     def __call__(self, x, nodenr=None):
         return self.execute(x, nodenr=nodenr)
 
-    def execute(self, x, benchmark=None, nodenr=None, out_dtype=np.float64, n_features=None):
+    def execute(self, x, benchmark=None, nodenr=None, out_dtype=np.float64, n_features=None, out=None):
         """``flow.execute(x, benchmark=...)``.
 
         x : (N, input_dim) array of uint8 / float32 / float64 (anything else is converted to float64).
         Returns a new (N, F) ``out_dtype`` array (float64 by default, like the reference);
         ``n_features`` keeps only the first features (the caller's ``sl[:, 0:D]``).
         ``benchmark`` is accepted for call compatibility; per-stage times are reported by ``stats()``.
+        ``out`` (optional) is a preallocated C-contiguous (N, F) float32/float64 array to fill, e.g. in
+        pinned memory, instead of allocating a fresh result like the reference does.
         """
         if nodenr is not None and nodenr != len(self) - 1:
             return self[:nodenr + 1].execute(x, out_dtype=out_dtype, n_features=n_features)
@@ -77,7 +79,12 @@ class GpuFlow(object):
             x = np.ascontiguousarray(x)
         ld = x.strides[0] // x.itemsize if x.shape[0] > 1 else x.shape[1]
         f = self.output_dim if n_features is None else int(n_features)
-        y = np.empty((x.shape[0], f), dtype=out_dtype)
+        if out is not None:
+            if out.shape != (x.shape[0], f) or not out.flags.c_contiguous or out.dtype not in (np.float32, np.float64):
+                raise ValueError("out must be a C-contiguous (%d, %d) float32/float64 array" % (x.shape[0], f))
+            y = out
+        else:
+            y = np.empty((x.shape[0], f), dtype=out_dtype)
         if x.shape[0] == 0:
             return y
         lib = _lib.load()

@@ -27,13 +27,12 @@ import numpy as np
 
 from . import expansions as ex
 
-KC = 16          # rows per expansion chunk (csrc/flow.cu)
 TILE = 128
 MAX_PASSES = 4
+WARPS = 8        # warps per CTA of layer_kernel (csrc/layer.cuh)
 DST_GLOBAL, DST_ROWS = 1, 2
-
-# (WM, WN, NT) per cfg code, see run_pass<> in csrc/flow.cu
-CFG = {0: (4, 1, 16), 1: (2, 2, 16), 2: (1, 4, 16), 3: (1, 4, 32)}
+SMEM_TARGET = 113 * 1024    # per-CTA shared memory that still lets two CTAs share an SM
+SMEM_LIMIT = 227 * 1024
 
 _SWITCHBOARDS = ("Switchboard", "Rectangular2dSwitchboard", "PInvSwitchboard", "DoubleRect2dSwitchboard",
                  "DoubleRhomb2dSwitchboard", "MeanInverseSwitchboard", "ChannelSwitchboard")
@@ -168,9 +167,9 @@ class _Lowerer(object):
     # -- helpers
     def _new_rows(self, n):
         """Shared-memory rows for an intermediate result of width n.  The producing pass stores its
-        padded width (``_choose_cfg``), so the allocation advances by that."""
+        padded width (``_choose_tile``), so the allocation advances by that."""
         r0 = self.n_rows
-        self.n_rows += _choose_cfg(n)[1]
+        self.n_rows += _padded_cols(n)
         return [self.prog.d_in + r0 + k for k in range(n)], r0
 
     def _shift_current(self, mean):
@@ -283,8 +282,8 @@ class _Lowerer(object):
 
         jp = self.j_pad if self.j_pad is not None else J
 
-        def padded(k, n):   # what the kernel executes: K rounded to the chunk, N to the register tile
-            return 2 * (-(-k // KC) * KC) * _choose_cfg(n)[1]
+        def padded(k, n):   # what the kernel executes: N rounded up to the register tiling
+            return 2 * k * _padded_cols(n)
 
         cost_two = padded(D, jp) + padded(d + (jp if recon else 0), P)
         # identity rows the folded form can reuse (only when the expansion reads x0 directly)
@@ -294,7 +293,7 @@ class _Lowerer(object):
                 if T["op"][k] == ex.OP_ID and int(T["i"][k]) not in id_row:
                     id_row[int(T["i"][k])] = k
         missing = [s for s in x_src if s not in id_row]
-        cost_fold = padded(D + len(missing), J + P) if J + P <= 128 else float("inf")
+        cost_fold = padded(D + len(missing), J + P) if J + P <= 256 else float("inf")
         mode = self.igsfa_mode
         if mode == "auto":
             mode = "fold" if cost_fold <= 1.1 * cost_two else "two_pass"
@@ -371,22 +370,37 @@ class OpSpec(object):
         self.passes = []        # list of dict(terms, W (n_w,K,Npad), b (n_w,Npad), dst, row0, cfg, n_valid, col_off, K_real, N_real)
         self.n_rows = 0
         self.twc = 1
+        self.npc = 1
+        self.n_runs = 1
+        self.runs = None
+        self.param_floats = 0
         self.alg_flops = 0
         self.exe_flops = 0
         self.mode = ""
         self.clip = (-np.inf, np.inf)   # saturation applied when results are stored to the output buffer
 
 
-def _choose_cfg(n_real):
-    if n_real <= 16:
-        return 0, 16
-    if n_real <= 32:
-        return 1, 32
-    if n_real <= 64:
-        return 2, -(-n_real // 16) * 16
-    if n_real <= 128:
-        return 3, -(-n_real // 32) * 32
-    raise UnsupportedFlow("a projection with %d output columns per node (max 128)" % n_real)
+def _choose_tile(n_real):
+    """(NT, NTL): columns per warp register tile and number of column tiles, NT * NTL >= n_real.
+
+    Minimises padded columns; on ties prefers NT <= 16 (register footprint that keeps two CTAs per SM),
+    then the larger NT (fewer shared-memory reads per FMA)."""
+    best = None
+    for ntl in (1, 2, 4, 8):
+        for nt in (8, 16, 24, 32):
+            if nt * ntl < n_real:
+                continue
+            key = (nt * ntl, nt > 16, -nt)
+            if best is None or key < best[0]:
+                best = (key, nt, ntl)
+    if best is None:
+        raise UnsupportedFlow("a projection with %d output columns per node (max 256)" % n_real)
+    return best[1], best[2]
+
+
+def _padded_cols(n_real):
+    nt, ntl = _choose_tile(n_real)
+    return nt * ntl
 
 
 def _assemble_layer(children, gather_cols, in_dim, igsfa_mode="auto"):
@@ -437,29 +451,25 @@ def _assemble_layer(children, gather_cols, in_dim, igsfa_mode="auto"):
     op.alg_flops = int(sum(p.alg_flops for p, _ in progs) * (n_nodes if shared else 1))
 
     row_cursor = 0
-    max_wm = 1
     for k in range(n_pass):
         plist = [p.passes[k] for p, _ in progs]
         t0 = plist[0].terms
         for q in plist[1:]:
             if len(q.terms) != len(t0) or not np.array_equal(q.terms, t0):
                 raise UnsupportedFlow("nodes of one Layer use different expansion tables")
-        K_real = len(t0)
-        K = -(-K_real // KC) * KC
+        K = len(t0)
         n_real = max(q.W.shape[1] for q in plist)
         to_rows = plist[0].to_rows
         pad_to = max([getattr(q, "pad_to", 0) for q in plist] + [n_real]) if to_rows else n_real
-        cfg, npad = _choose_cfg(max(n_real, pad_to))
-        terms = np.zeros(K, dtype=ex.TERM_DTYPE)
-        terms[:K_real] = t0
-        terms["i"][K_real:] = t0["i"][0] if K_real else 0   # padded rows: any valid source, zero weights
+        nt, ntl = _choose_tile(max(n_real, pad_to))
+        npad = nt * ntl
         n_w = len(plist)
         W = np.zeros((n_w, K, npad))
         b = np.zeros((n_w, npad))
         n_valid = np.zeros(n_nodes, dtype=np.int32)
         col_off = np.zeros(n_nodes, dtype=np.int32)
         for w_i, q in enumerate(plist):
-            W[w_i, :K_real, :q.W.shape[1]] = q.W
+            W[w_i, :, :q.W.shape[1]] = q.W
             b[w_i, :q.W.shape[1]] = q.b
         for nd in range(n_nodes):
             q = plist[0 if shared else nd]
@@ -473,13 +483,85 @@ def _assemble_layer(children, gather_cols, in_dim, igsfa_mode="auto"):
             if any(q.row0 != row0 for q in plist):
                 raise UnsupportedFlow("nodes of one Layer produce intermediate results of different widths")
             row_cursor += npad
-        op.passes.append(dict(terms=terms, W=W, b=b, dst=dst, row0=row0, cfg=cfg, n_valid=n_valid,
-                              col_off=col_off, K_real=K_real, N_real=n_real, K=K, Npad=npad))
-        max_wm = max(max_wm, CFG[cfg][0])
+        op.passes.append(dict(terms=t0.copy(), W=W, b=b, dst=dst, row0=row0, NT=nt, NTL=ntl, n_valid=n_valid,
+                              col_off=col_off, K_real=K, N_real=n_real, K=K, Npad=npad))
         op.exe_flops += n_nodes * 2 * K * npad
     op.n_rows = row_cursor
-    op.twc = max_wm
+    _decompose(op)
     return op
+
+
+def _gather_runs(gather_row):
+    """Contiguous feature runs of one receptive field: list of (i0, f0, len)."""
+    g = np.asarray(gather_row, dtype=np.int64)
+    runs = []
+    i0 = 0
+    for i in range(1, len(g) + 1):
+        if i == len(g) or g[i] != g[i - 1] + 1:
+            runs.append((i0, int(g[i0]), i - i0))
+            i0 = i
+    return runs
+
+
+def _op_smem(op, twc, el=4, stages=1):
+    """Shared memory of layer_kernel for this op (mirrors layout_op in csrc/flow.cu)."""
+    def up(x):
+        return (x + 127) // 128 * 128
+    n_terms = sum(ps["K"] for ps in op.passes)
+    scratch = max([(WARPS // 2) * ps["NT"] * TILE * 4 for ps in op.passes if _pass_split(ps, twc)[1] > 1] + [0])
+    raw = op.d_in * TILE * el
+    stage = up(twc * raw + op.param_floats * 4)
+    return 128 + up(n_terms * 8) + up(twc * op.n_rows * TILE * 4) + up(scratch) + stages * stage
+
+
+def _pass_split(ps, twc):
+    """(TW, KS): tile slots processed concurrently and K-split so that TW * NTL * KS == WARPS."""
+    tw = min(twc, WARPS // ps["NTL"])
+    return tw, WARPS // (ps["NTL"] * tw)
+
+
+def _decompose(op):
+    """Choose tile slots per CTA, nodes per CTA and the per-pass warp decomposition."""
+    d_pad = -(-op.d_in // 4) * 4
+    off = d_pad
+    for ps in op.passes:
+        ps["b_off"] = off
+        off += ps["Npad"]
+        ps["w_off"] = off
+        off += ps["K"] * ps["Npad"]
+    op.param_floats = -(-off // 4) * 4
+    fits = [t for t in (8, 4, 2, 1) if _op_smem(op, t) <= SMEM_TARGET]
+    if fits:
+        op.twc = fits[0]
+    else:
+        fits = [t for t in (8, 4, 2, 1) if _op_smem(op, t) <= SMEM_LIMIT]
+        if not fits:
+            raise UnsupportedFlow("a receptive field of %d inputs does not fit in shared memory" % op.d_in)
+        op.twc = fits[0]
+    for ps in op.passes:
+        ps["TW"], ps["KS"] = _pass_split(ps, op.twc)
+    op.npc = max(1, min(8, op.n_nodes // 32))
+    runs = [_gather_runs(g) for g in op.gather]
+    op.n_runs = max(len(r) for r in runs)
+    op.runs = np.zeros((op.n_nodes, op.n_runs, 4), dtype=np.int32)
+    for nd, rl in enumerate(runs):
+        for r, (i0, f0, ln) in enumerate(rl):
+            op.runs[nd, r] = (i0, f0, ln, 0)
+
+
+def _segments(terms):
+    """Runs of consecutive terms sharing (op, exponent): list of (op, k0, k1, p)."""
+    segs = []
+    k0 = 0
+    for k in range(1, len(terms) + 1):
+        same = k < len(terms) and terms["op"][k] == terms["op"][k0] and (
+            terms["op"][k] in (ex.OP_ID, ex.OP_MUL, ex.OP_MUL3, ex.OP_ABS) or terms["p"][k] == terms["p"][k0])
+        if not same:
+            op_code = int(terms["op"][k0])
+            p = 0.0 if op_code in (ex.OP_ID, ex.OP_MUL, ex.OP_MUL3, ex.OP_ABS) else float(terms["p"][k0])
+            segs.append((op_code, k0, k, p))
+            k0 = k
+    return segs
 
 
 # --------------------------------------------------------------------------------------------------
@@ -606,10 +688,11 @@ def _copy_op(cols, in_dim):
     n_valid = np.full(n_nodes, 16, dtype=np.int32)
     n_valid[-1] = n - 16 * (n_nodes - 1)
     op.passes = [dict(terms=_identity_terms(range(16)), W=np.eye(16)[None], b=np.zeros((1, 16)), dst=DST_GLOBAL,
-                      row0=0, cfg=0, n_valid=n_valid, col_off=np.zeros(n_nodes, dtype=np.int32), K_real=16,
+                      row0=0, NT=16, NTL=1, n_valid=n_valid, col_off=np.zeros(n_nodes, dtype=np.int32), K_real=16,
                       N_real=16, K=16, Npad=16)]
-    op.n_rows, op.twc, op.mode = 0, 4, "copy"
+    op.n_rows, op.mode = 0, "copy"
     op.exe_flops = n_nodes * 2 * 16 * 16
+    _decompose(op)
     return op
 
 
@@ -625,22 +708,44 @@ def _arr(a, dtype):
 
 
 def serialize(spec):
+    """Plan blob, version 2 (parsed by hgsfa_plan_create in csrc/flow.cu; layout in DESIGN.md section 4)."""
     last_dim = spec.ops[-1].out_dim
-    out = [b"HGSFAPL1" + struct.pack("<7q", spec.input_dim, last_dim, len(spec.ops), 0, 0, 0, 0)]
+    out = [b"HGSFAPL2" + struct.pack("<7q", spec.input_dim, last_dim, len(spec.ops), 0, 0, 0, 0)]
     assert len(out[0]) == 64
     for op in spec.ops:
-        hdr = [op.n_nodes, op.d_in, op.in_dim, op.out_dim, len(op.passes), int(op.shared), op.n_rows, op.twc,
-               op.alg_flops, op.exe_flops, 0, 0]
-        out.append(struct.pack("<12q", *hdr) + struct.pack("<4d", float(op.clip[0]), float(op.clip[1]), 0.0, 0.0))
-        out.append(_arr(op.gather, np.int32))
-        out.append(_arr(op.in_offset, np.float32))
+        n_w = 1 if op.shared else op.n_nodes
+        n_terms = sum(ps["K"] for ps in op.passes)
+        out.append(struct.pack("<12q", op.n_nodes, op.d_in, op.in_dim, op.out_dim, len(op.passes), int(op.shared),
+                               op.n_rows, op.twc, op.alg_flops, op.exe_flops, op.npc, op.n_runs)
+                   + struct.pack("<2d", float(op.clip[0]), float(op.clip[1]))
+                   + struct.pack("<2q", op.param_floats, n_terms))
+        out.append(_arr(op.runs, np.int32))
         out.append(_arr(op.out_col, np.int32))
+        params = np.zeros((n_w, op.param_floats), dtype=np.float32)
+        params[:, :op.d_in] = op.in_offset
+        t16 = np.zeros((n_terms, 4), dtype=np.int16)
+        t_off = 0
         for ps in op.passes:
-            out.append(struct.pack("<8q", ps["K"], ps["Npad"], ps["dst"], ps["row0"], ps["cfg"], ps["K_real"],
-                                   ps["N_real"], 0))
-            out.append(_arr(ps["terms"], ex.TERM_DTYPE))
-            out.append(_arr(ps["W"], np.float32))
-            out.append(_arr(ps["b"], np.float32))
+            params[:, ps["b_off"]:ps["b_off"] + ps["Npad"]] = ps["b"]
+            params[:, ps["w_off"]:ps["w_off"] + ps["K"] * ps["Npad"]] = ps["W"].reshape(n_w, -1)
+            t = ps["terms"]
+            t16[t_off:t_off + ps["K"], 0] = t["i"]
+            two = (t["op"] == ex.OP_MUL) | (t["op"] == ex.OP_MUL3)
+            t16[t_off:t_off + ps["K"], 1] = np.where(two, t["j"], 0)
+            t16[t_off:t_off + ps["K"], 2] = np.where(t["op"] == ex.OP_MUL3, t["p"].astype(np.int64), 0)
+            ps["term_off"] = t_off
+            t_off += ps["K"]
+        if not np.isfinite(params).all():
+            raise ValueError("non-finite flow parameters")
+        out.append(_arr(params, np.float32))
+        out.append(_arr(t16, np.int16))
+        for ps in op.passes:
+            segs = _segments(ps["terms"])
+            out.append(struct.pack("<16q", ps["K"], ps["Npad"], ps["NT"], ps["NTL"], ps["KS"], ps["TW"], ps["dst"],
+                                   ps["row0"], ps["w_off"], ps["b_off"], ps["term_off"], len(segs), ps["K_real"],
+                                   ps["N_real"], 0, 0))
+            sb = b"".join(struct.pack("<3if", o, k0, k1, p) for (o, k0, k1, p) in segs)
+            out.append(_pad16(sb))
             out.append(_arr(ps["n_valid"], np.int32))
             out.append(_arr(ps["col_off"], np.int32))
     return b"".join(out)
@@ -650,8 +755,9 @@ def describe(spec):
     lines = ["plan: %d -> %d, %d ops, %.3f MFLOP/window algorithmic, %.3f executed"
              % (spec.input_dim, spec.output_dim, len(spec.ops), spec.alg_flops / 1e6, spec.exe_flops / 1e6)]
     for k, op in enumerate(spec.ops):
-        ps = ", ".join("K%d->N%d(cfg%d)" % (p["K_real"], p["N_real"], p["cfg"]) for p in op.passes)
-        lines.append("  op%-2d nodes=%-4d d_in=%-4d out=%-5d %s %s [%s] twc=%d rows=%d"
+        ps = ", ".join("K%d->N%d(%dx%d ks%d tw%d)" % (p["K_real"], p["N_real"], p["NT"], p["NTL"], p["KS"], p["TW"])
+                       for p in op.passes)
+        lines.append("  op%-2d nodes=%-4d d_in=%-4d out=%-5d %s %s [%s] twc=%d npc=%d runs=%d rows=%d smem=%dK"
                      % (k, op.n_nodes, op.d_in, op.out_dim, "clone" if op.shared else "layer", op.mode, ps,
-                        op.twc, op.n_rows))
+                        op.twc, op.npc, op.n_runs, op.n_rows, _op_smem(op, op.twc) // 1024))
     return "\n".join(lines)
