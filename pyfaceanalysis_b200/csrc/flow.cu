@@ -215,7 +215,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
     d.param_floats = (int)oh[14]; d.n_terms = (int)oh[15];
     const bool sane = d.n_nodes > 0 && d.n_nodes <= 65535 * 64 && d.d_in > 0 && d.d_in < 32768 && d.in_dim == cur_dim &&
                       d.out_dim > 0 && d.n_passes >= 1 && d.n_passes <= MAX_PASSES &&
-                      (d.twc == 1 || d.twc == 2 || d.twc == 4 || d.twc == 8) && d.n_rows >= 0 && d.npc >= 1 &&
+                      (d.twc == 1 || d.twc == 2 || d.twc == 4 || d.twc == 8 || d.twc == 16) && d.n_rows >= 0 && d.npc >= 1 &&
                       d.n_runs >= 1 && d.n_runs <= d.d_in && d.param_floats > 0 && d.param_floats % 4 == 0 &&
                       d.n_terms > 0;
     if (!sane)
@@ -253,10 +253,11 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       PassDev& dp = d.pass[p];
       dp.K = (int)ph[0]; dp.Npad = (int)ph[1]; dp.NT = (int)ph[2]; dp.NTL = (int)ph[3]; dp.KS = (int)ph[4];
       dp.TW = (int)ph[5]; dp.dst = (int)ph[6]; dp.row0 = (int)ph[7]; dp.w_off = (int)ph[8]; dp.b_off = (int)ph[9];
-      dp.term_off = (int)ph[10]; dp.n_seg = (int)ph[11];
+      dp.term_off = (int)ph[10]; dp.n_seg = (int)ph[11]; dp.SW = (int)ph[14];
       const bool psane =
           dp.K > 0 && (dp.NT == 8 || dp.NT == 16 || dp.NT == 24 || dp.NT == 32) && dp.NTL >= 1 && dp.KS >= 1 &&
-          dp.TW >= 1 && dp.NTL * dp.KS * dp.TW == WARPS && dp.Npad == dp.NT * dp.NTL && d.twc % dp.TW == 0 &&
+          dp.TW >= 1 && dp.NTL * dp.KS * dp.TW == WARPS && dp.Npad == dp.NT * dp.NTL && (dp.SW == 1 || dp.SW == 2) &&
+          (dp.SW == 1 || dp.NT <= 16) && d.twc % dp.SW == 0 &&
           (dp.KS & (dp.KS - 1)) == 0 && (dp.dst & (DST_GLOBAL | DST_ROWS)) && dp.row0 >= 0 &&
           (!(dp.dst & DST_ROWS) || dp.row0 + dp.Npad <= d.n_rows) && dp.w_off >= 0 && dp.w_off % 4 == 0 && dp.b_off >= 0 &&
           dp.w_off + dp.K * dp.Npad <= d.param_floats && dp.b_off + dp.Npad <= d.param_floats && dp.term_off >= 0 &&
@@ -270,7 +271,11 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       if (!cur.ok) break;
       int kcov = 0;
       for (int sgi = 0; sgi < dp.n_seg; ++sgi) {
-        if (segs[sgi].op < 0 || segs[sgi].op > OP_CLIP || segs[sgi].k0 != kcov || segs[sgi].k1 < segs[sgi].k0)
+        if (segs[sgi].op < 0 || segs[sgi].op > OP_CLIP || segs[sgi].k0 != kcov || segs[sgi].k1 < segs[sgi].k0 ||
+            segs[sgi].kind < 0 || segs[sgi].kind > 2 ||
+            (segs[sgi].ibase >= 0 && segs[sgi].ibase + (segs[sgi].k1 - segs[sgi].k0) > d.d_in + d.n_rows) ||
+            (segs[sgi].ibase >= 0 && segs[sgi].kind == 0 && segs[sgi].ibase + (segs[sgi].k1 - segs[sgi].k0) > d.d_in) ||
+            (segs[sgi].ibase >= 0 && segs[sgi].kind == 1 && segs[sgi].ibase < d.d_in))
           return plan_fail(pl, "op %lld pass %d: bad term segment %d", (long long)o, p, sgi);
         kcov = segs[sgi].k1;
       }
@@ -282,8 +287,8 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       dp.segs = reinterpret_cast<const Seg*>(dev_ptr(segs));
       dp.n_valid = reinterpret_cast<const int*>(dev_ptr(n_valid));
       dp.col_off = reinterpret_cast<const int*>(dev_ptr(col_off));
-      if (dp.NT > 16) op.wide = true;
-      if (dp.KS > 1) op.scratch_floats = std::max(op.scratch_floats, (WARPS / 2) * dp.NT * TILE);
+      if (dp.NT * dp.SW > 16) op.wide = true;
+      if (dp.KS > 1) op.scratch_floats = std::max(op.scratch_floats, (WARPS / 2) * dp.SW * dp.NT * TILE);
     }
     if (!cur.ok) break;
     for (int v = 0; v < 2; ++v) {

@@ -36,11 +36,15 @@ enum TermOp { OP_ID = 0, OP_MUL = 1, OP_ABSPOW = 2, OP_SGNPOW = 3, OP_MUL3 = 4, 
 enum { DST_GLOBAL = 1, DST_ROWS = 2 };
 
 struct Term16 { int16_t i, j, k, pad; };        // source rows of one expansion term
-struct Seg { int32_t op, k0, k1; float p; };    // run of terms [k0, k1) sharing one op (and exponent)
+// run of terms [k0, k1) sharing one op (and exponent).  kind: 0 = all operands are receptive-field rows,
+// 1 = all operands are shared rows of an earlier pass, 2 = mixed.  ibase >= 0: operand i of term k is
+// row ibase + (k - k0) (no term-table lookup), else read from the term table.
+struct Seg { int32_t op, k0, k1; float p; int32_t kind, ibase, nomean, pad1; };   // nomean: x_mean is folded into the bias
 struct Run { int32_t i0, f0, len, pad; };       // rows [i0, i0+len) of x0 = features [f0, f0+len) of the input
 
 struct PassDev {
-  int K, Npad, NT, NTL, KS, TW;   // contraction size, padded columns, columns per warp, column tiles, K-split, tile slots per round
+  int K, Npad, NT, NTL, KS, TW, SW;   // contraction size, padded columns, columns per warp, column tiles, K-split,
+                                      // slot groups per round, tile slots per warp (register tile = SW*4 windows x NT)
   int dst, row0;                  // destination flags, first shared row
   int w_off, b_off;               // float offsets of W[K][Npad] and b[Npad] inside the node parameter block
   int term_off, n_seg;
@@ -114,53 +118,195 @@ __device__ __forceinline__ float2 unpack2(unsigned long long v) {
 }
 
 __device__ __forceinline__ float abspow(float x, float p) {
-  return exp2f(p * __log2f(fabsf(x)));   // |x|^p, p > 0: lg2(0) = -inf -> ex2(-inf) = 0
+  // |x|^p, p > 0, on the raw MUFU approximations (lg2(0) = -inf -> ex2(-inf) = 0); .ftz: operands are
+  // pixel / feature magnitudes, never denormal in a way that matters at 1e-3 x std
+  float l, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fabsf(x)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p * l));
+  return r;
 }
 __device__ __forceinline__ float4 clamp4(float4 v, float lo, float hi) {
   return make_float4(fminf(fmaxf(v.x, lo), hi), fminf(fmaxf(v.y, lo), hi), fminf(fmaxf(v.z, lo), hi),
                      fminf(fmaxf(v.w, lo), hi));
 }
+// 4 packed uint8 -> 4 floats without the XU-pipe I2F: splice each byte into the mantissa of 2^23
+__device__ __forceinline__ float4 u8x4_to_float4(uint32_t u) {
+  const float magic = 8388608.0f;
+  return make_float4(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7650)) - magic,
+                     __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7651)) - magic,
+                     __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7652)) - magic,
+                     __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7653)) - magic);
+}
 
 // ------------------------------------------------------------------------------------------------
 // operand fetch: row i of the node's source space for this lane's 4 windows
-//   i <  d_in : receptive-field row (IN_T in the staged buffer), minus x_mean[i]
-//   i >= d_in : shared row written by an earlier pass (float)
+//   raw(i)  : receptive-field row i (IN_T in the staged buffer), minus x_mean[i]
+//   srow(r) : shared row r written by an earlier pass (float)
 // ------------------------------------------------------------------------------------------------
 template <typename IN_T>
 struct Rows {
-  const IN_T* raw;      // [d_in][128] of this tile slot
-  const float* srow;    // [n_rows][128] of this tile slot
+  const IN_T* rawp;     // [d_in][128] of this tile slot, already offset to this lane's 4 windows
+  const float* srowp;   // [n_rows][128] of this tile slot, already offset to this lane's 4 windows
   const float* mean;    // [d_in] in the staged parameter block
-  int d_in, lane;
-  __device__ __forceinline__ float4 operator()(int i) const {
-    if (i < d_in) {
-      float4 v;
-      if (sizeof(IN_T) == 1) {
-        const uchar4 u = reinterpret_cast<const uchar4*>(raw)[i * (TILE / 4) + lane];
-        v = make_float4(float(u.x), float(u.y), float(u.z), float(u.w));
-      } else {
-        v = reinterpret_cast<const float4*>(raw)[i * (TILE / 4) + lane];
-      }
-      const float m = mean[i];
-      v.x -= m; v.y -= m; v.z -= m; v.w -= m;
-      return v;
-    }
-    return reinterpret_cast<const float4*>(srow)[(i - d_in) * (TILE / 4) + lane];
+  int d_in;
+  __device__ __forceinline__ float4 raw_nomean(int i) const {
+    if (sizeof(IN_T) == 1) return u8x4_to_float4(*reinterpret_cast<const uint32_t*>(rawp + size_t(i) * TILE));
+    return *reinterpret_cast<const float4*>(rawp + size_t(i) * TILE);
   }
+  __device__ __forceinline__ float4 raw(int i) const {
+    float4 v = raw_nomean(i);
+    const float m = mean[i];
+    v.x -= m; v.y -= m; v.z -= m; v.w -= m;
+    return v;
+  }
+  __device__ __forceinline__ float4 srow(int r) const { return *reinterpret_cast<const float4*>(srowp + size_t(r) * TILE); }
+  __device__ __forceinline__ float4 any(int i) const { return i < d_in ? raw(i) : srow(i - d_in); }
 };
 
-template <int NT>
-__device__ __forceinline__ void fma_row(unsigned long long (&acc)[4][NT / 2], const float4 a, const float* wrow) {
-  const unsigned long long ax = dup2(a.x), ay = dup2(a.y), az = dup2(a.z), aw = dup2(a.w);
+// acc[s][r][q] += a[s].r * (w[2q], w[2q+1]) for the SW tile slots of this warp; the weight row is read once
+template <int NT, int SW>
+__device__ __forceinline__ void fma_row(unsigned long long (&acc)[SW][4][NT / 2], const float4 (&a)[SW], const float* wrow) {
   const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(wrow);
 #pragma unroll
   for (int q = 0; q < NT / 4; ++q) {
     const ulonglong2 w = w2[q];
-    ffma2(acc[0][2 * q], ax, w.x); ffma2(acc[0][2 * q + 1], ax, w.y);
-    ffma2(acc[1][2 * q], ay, w.x); ffma2(acc[1][2 * q + 1], ay, w.y);
-    ffma2(acc[2][2 * q], az, w.x); ffma2(acc[2][2 * q + 1], az, w.y);
-    ffma2(acc[3][2 * q], aw, w.x); ffma2(acc[3][2 * q + 1], aw, w.y);
+#pragma unroll
+    for (int s = 0; s < SW; ++s) {
+      const unsigned long long ax = dup2(a[s].x), ay = dup2(a[s].y), az = dup2(a[s].z), aw = dup2(a[s].w);
+      ffma2(acc[s][0][2 * q], ax, w.x); ffma2(acc[s][0][2 * q + 1], ax, w.y);
+      ffma2(acc[s][1][2 * q], ay, w.x); ffma2(acc[s][1][2 * q + 1], ay, w.y);
+      ffma2(acc[s][2][2 * q], az, w.x); ffma2(acc[s][2][2 * q + 1], az, w.y);
+      ffma2(acc[s][3][2 * q], aw, w.x); ffma2(acc[s][3][2 * q + 1], aw, w.y);
+    }
   }
+}
+
+__device__ __forceinline__ float4 pow4(const float4 a, float p) {
+  return make_float4(abspow(a.x, p), abspow(a.y, p), abspow(a.z, p), abspow(a.w, p));
+}
+__device__ __forceinline__ float4 mul4(const float4 a, const float4 b) {
+  return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// software-pipelined row loop.  A warp issues in order, so an operand chain (LDS -> convert -> pow)
+// placed right before the FMAs that need it stalls the whole warp.  Each step therefore
+//   (A) issues the shared-memory loads of row it+2,
+//   (B) converts / expands the operands of row it+1 (loaded one step earlier) and loads its weights,
+//   (C) runs the FMAs of row it,
+// so every dependent instruction finds its inputs at least one full row of FMAs old.
+// ------------------------------------------------------------------------------------------------
+enum SegMode { M_ID_NOMEAN = 0, M_ID_MEAN = 1, M_ID_SROW = 2, M_POW = 3, M_MUL = 4 };
+
+template <int NT>
+struct WReg { ulonglong2 q[NT / 4]; };
+
+template <int NT>
+__device__ __forceinline__ void load_w(WReg<NT>& w, const float* wrow) {
+  const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(wrow);
+#pragma unroll
+  for (int q = 0; q < NT / 4; ++q) w.q[q] = w2[q];
+}
+
+template <int NT, int SW>
+__device__ __forceinline__ void fma_regs(unsigned long long (&acc)[SW][4][NT / 2], const float4 (&a)[SW], const WReg<NT>& w) {
+#pragma unroll
+  for (int s = 0; s < SW; ++s) {
+    const unsigned long long ax = dup2(a[s].x), ay = dup2(a[s].y), az = dup2(a[s].z), aw = dup2(a[s].w);
+#pragma unroll
+    for (int q = 0; q < NT / 4; ++q) {
+      ffma2(acc[s][0][2 * q], ax, w.q[q].x); ffma2(acc[s][0][2 * q + 1], ax, w.q[q].y);
+      ffma2(acc[s][1][2 * q], ay, w.q[q].x); ffma2(acc[s][1][2 * q + 1], ay, w.q[q].y);
+      ffma2(acc[s][2][2 * q], az, w.q[q].x); ffma2(acc[s][2][2 * q + 1], az, w.q[q].y);
+      ffma2(acc[s][3][2 * q], aw, w.q[q].x); ffma2(acc[s][3][2 * q + 1], aw, w.q[q].y);
+    }
+  }
+}
+
+// un-converted operands of one row for SW slots
+template <typename IN_T, int SW, int MODE>
+struct RawRow {
+  float4 f[SW];     // float sources (f32 rows / shared rows), or first operand of a product
+  float4 g[SW];     // second operand of a product
+  uint32_t u[SW];   // uint8 sources
+  uint32_t v[SW];
+  float m, m2;      // x_mean of the row(s)
+};
+
+template <typename IN_T, int SW, int MODE>
+__device__ __forceinline__ void load_raw(RawRow<IN_T, SW, MODE>& r, const Rows<IN_T> (&rows)[SW], int i, int j) {
+#pragma unroll
+  for (int s = 0; s < SW; ++s) {
+    if (MODE == M_ID_SROW) {
+      r.f[s] = *reinterpret_cast<const float4*>(rows[s].srowp + size_t(i) * TILE);
+    } else if (sizeof(IN_T) == 1) {
+      r.u[s] = *reinterpret_cast<const uint32_t*>(rows[s].rawp + size_t(i) * TILE);
+      if (MODE == M_MUL) r.v[s] = *reinterpret_cast<const uint32_t*>(rows[s].rawp + size_t(j) * TILE);
+    } else {
+      r.f[s] = *reinterpret_cast<const float4*>(rows[s].rawp + size_t(i) * TILE);
+      if (MODE == M_MUL) r.g[s] = *reinterpret_cast<const float4*>(rows[s].rawp + size_t(j) * TILE);
+    }
+  }
+  if (MODE == M_ID_MEAN || MODE == M_POW || MODE == M_MUL) r.m = rows[0].mean[i];
+  if (MODE == M_MUL) r.m2 = rows[0].mean[j];
+}
+
+__device__ __forceinline__ float4 sub4(float4 v, float m) { return make_float4(v.x - m, v.y - m, v.z - m, v.w - m); }
+
+template <typename IN_T, int SW, int MODE>
+__device__ __forceinline__ void convert_raw(float4 (&a)[SW], const RawRow<IN_T, SW, MODE>& r, float p) {
+#pragma unroll
+  for (int s = 0; s < SW; ++s) {
+    float4 x = (MODE != M_ID_SROW && sizeof(IN_T) == 1) ? u8x4_to_float4(r.u[s]) : r.f[s];
+    if (MODE == M_ID_MEAN || MODE == M_POW || MODE == M_MUL) x = sub4(x, r.m);
+    if (MODE == M_POW) x = pow4(x, p);
+    if (MODE == M_MUL) {
+      float4 y = (sizeof(IN_T) == 1) ? u8x4_to_float4(r.v[s]) : r.g[s];
+      x = mul4(x, sub4(y, r.m2));
+    }
+    a[s] = x;
+  }
+}
+
+// rows i0, i0+istep, ... (n of them); weights w0, w0+wstep, ...; for M_MUL the operand rows come from
+// the term table (terms[0], terms[tstep], ...)
+template <typename IN_T, int NT, int SW, int MODE>
+__device__ __forceinline__ void seg_pipeline(unsigned long long (&acc)[SW][4][NT / 2], const Rows<IN_T> (&rows)[SW],
+                                             const float* w0, int wstep, int i0, int istep, int n, float p,
+                                             const Term16* terms, int tstep) {
+  if (n <= 0) return;
+  RawRow<IN_T, SW, MODE> R[2];
+  float4 a[2][SW];
+  WReg<NT> w[2];
+  auto row_ij = [&](int it, int& i, int& j) {
+    const int c = min(it, n - 1);          // clamped: the pipeline over-fetches up to two rows
+    if (MODE == M_MUL) {
+      const Term16 t = terms[c * tstep];
+      i = t.i; j = t.j;
+    } else {
+      i = i0 + c * istep; j = 0;
+    }
+  };
+  int i, j;
+  row_ij(0, i, j); load_raw<IN_T, SW, MODE>(R[0], rows, i, j);
+  row_ij(1, i, j); load_raw<IN_T, SW, MODE>(R[1], rows, i, j);
+  load_w<NT>(w[0], w0);
+  convert_raw<IN_T, SW, MODE>(a[0], R[0], p);
+  int it = 0;
+#pragma unroll 1
+  for (; it + 1 < n; it += 2) {
+    // step it (parity 0)
+    row_ij(it + 2, i, j); load_raw<IN_T, SW, MODE>(R[0], rows, i, j);
+    load_w<NT>(w[1], w0 + min(it + 1, n - 1) * wstep);
+    convert_raw<IN_T, SW, MODE>(a[1], R[1], p);
+    fma_regs<NT, SW>(acc, a[0], w[0]);
+    // step it + 1 (parity 1)
+    row_ij(it + 3, i, j); load_raw<IN_T, SW, MODE>(R[1], rows, i, j);
+    load_w<NT>(w[0], w0 + min(it + 2, n - 1) * wstep);
+    convert_raw<IN_T, SW, MODE>(a[0], R[0], p);
+    fma_regs<NT, SW>(acc, a[1], w[1]);
+  }
+  if (it < n) fma_regs<NT, SW>(acc, a[0], w[0]);
 }
 
 // bias + saturation + store of 4 windows x 1 column
@@ -182,7 +328,7 @@ struct Epilogue {
   }
 };
 
-template <typename IN_T, int NT>
+template <typename IN_T, int NT, int SW>
 __device__ __forceinline__ void run_pass(const OpDev& op, const PassDev& ps, int node, int64_t tile0, int64_t ntiles,
                                          const uint8_t* stage, uint8_t* smem, float* __restrict__ xout) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,132 +343,133 @@ __device__ __forceinline__ void run_pass(const OpDev& op, const PassDev& ps, int
   const int nvalid = (ps.dst & DST_GLOBAL) ? __ldg(ps.n_valid + node) : 0;
   const int col0 = (ps.dst & DST_GLOBAL) ? (__ldg(op.out_col + node) + __ldg(ps.col_off + node)) : 0;
   const int Npad = ps.Npad, KS = ps.KS;
+  const int wstep = KS * Npad;
 
-  for (int r0 = 0; r0 < op.twc; r0 += ps.TW) {
-    const int slot = r0 + tw;
-    const int64_t tile = tile0 + slot;
-    const bool active = tw < ps.TW && slot < op.twc && tile < ntiles && n0 < Npad;
-    float* srow = reinterpret_cast<float*>(smem + op.sm_srows) + size_t(slot) * op.n_rows * TILE;
-    unsigned long long acc[4][NT / 2];
+  for (int g0 = 0; g0 < op.twc; g0 += ps.TW * SW) {
+    const int slot0 = g0 + tw * SW;
+    const bool active = slot0 < op.twc && tile0 + slot0 < ntiles && n0 < Npad;
+    unsigned long long acc[SW][4][NT / 2];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int s = 0; s < SW; ++s)
 #pragma unroll
-      for (int q = 0; q < NT / 2; ++q) acc[r][q] = 0ull;
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < NT / 2; ++q) acc[s][r][q] = 0ull;
 
     if (active) {
-      Rows<IN_T> rows{reinterpret_cast<const IN_T*>(stage + size_t(slot) * op.sm_raw_bytes), srow, params, op.d_in, lane};
-      for (int s = 0; s < ps.n_seg; ++s) {
-        const Seg sg = ps.segs[s];
+      Rows<IN_T> rows[SW];
+#pragma unroll
+      for (int s = 0; s < SW; ++s) {
+        // a slot past the end of the batch holds stale shared memory: computed, never stored
+        const int slot = min(slot0 + s, op.twc - 1);
+        rows[s].rawp = reinterpret_cast<const IN_T*>(stage + size_t(slot) * op.sm_raw_bytes) + lane * 4;
+        rows[s].srowp = reinterpret_cast<const float*>(smem + op.sm_srows) + size_t(slot) * op.n_rows * TILE + lane * 4;
+        rows[s].mean = params;
+        rows[s].d_in = op.d_in;
+      }
+      for (int sgi = 0; sgi < ps.n_seg; ++sgi) {
+        const Seg sg = ps.segs[sgi];
         const int kb = sg.k0 + ks;
-        switch (sg.op) {
-          case OP_ID:
-#pragma unroll 2
-            for (int k = kb; k < sg.k1; k += KS) fma_row<NT>(acc, rows(terms[k].i), W + k * Npad);
-            break;
-          case OP_MUL:
-#pragma unroll 2
-            for (int k = kb; k < sg.k1; k += KS) {
-              const Term16 t = terms[k];
-              const float4 a = rows(t.i), b = rows(t.j);
-              fma_row<NT>(acc, make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w), W + k * Npad);
+        const float* w = W + kb * Npad;
+        float4 a[SW];
+        const int n_rows_here = (sg.k1 - kb + KS - 1) / KS;   // rows of this segment owned by this K-split part
+        if (sg.op == OP_ID && sg.kind == 0 && sg.ibase >= 0 && sg.nomean) {
+          seg_pipeline<IN_T, NT, SW, M_ID_NOMEAN>(acc, rows, w, wstep, sg.ibase + ks, KS, n_rows_here, 0.f, terms, 0);
+        } else if (sg.op == OP_ID && sg.kind == 0 && sg.ibase >= 0) {
+          seg_pipeline<IN_T, NT, SW, M_ID_MEAN>(acc, rows, w, wstep, sg.ibase + ks, KS, n_rows_here, 0.f, terms, 0);
+        } else if (sg.op == OP_ID && sg.kind == 1 && sg.ibase >= 0) {
+          seg_pipeline<IN_T, NT, SW, M_ID_SROW>(acc, rows, w, wstep, sg.ibase - op.d_in + ks, KS, n_rows_here, 0.f, terms, 0);
+        } else if (sg.op == OP_ABSPOW && sg.kind == 0 && sg.ibase >= 0) {
+          seg_pipeline<IN_T, NT, SW, M_POW>(acc, rows, w, wstep, sg.ibase + ks, KS, n_rows_here, sg.p, terms, 0);
+        } else if (sg.op == OP_MUL && sg.kind == 0) {
+          seg_pipeline<IN_T, NT, SW, M_MUL>(acc, rows, w, wstep, 0, 0, n_rows_here, 0.f, terms + kb, KS);
+        } else {
+          // everything else (rare): generic operand fetch, one term at a time
+          for (int k = kb; k < sg.k1; k += KS, w += wstep) {
+            const Term16 t = terms[k];
+            const int i = sg.ibase >= 0 ? sg.ibase + (k - sg.k0) : int(t.i);
+#pragma unroll
+            for (int s = 0; s < SW; ++s) {
+              const float4 x = rows[s].any(i);
+              float4 v;
+              switch (sg.op) {
+                case OP_ID: v = x; break;
+                case OP_MUL: v = mul4(x, rows[s].any(t.j)); break;
+                case OP_ABSPOW: v = pow4(x, sg.p); break;
+                case OP_SGNPOW: {
+                  const float4 m = pow4(x, sg.p);
+                  v = make_float4(copysignf(m.x, x.x), copysignf(m.y, x.y), copysignf(m.z, x.z), copysignf(m.w, x.w));
+                  break;
+                }
+                case OP_MUL3: v = mul4(mul4(x, rows[s].any(t.j)), rows[s].any(t.k)); break;
+                case OP_ABS: v = make_float4(fabsf(x.x), fabsf(x.y), fabsf(x.z), fabsf(x.w)); break;
+                case OP_CLIP: v = clamp4(x, -sg.p, sg.p); break;
+                default: v = make_float4(0.f, 0.f, 0.f, 0.f); break;
+              }
+              a[s] = v;
             }
-            break;
-          case OP_ABSPOW:
-#pragma unroll 2
-            for (int k = kb; k < sg.k1; k += KS) {
-              const float4 a = rows(terms[k].i);
-              fma_row<NT>(acc, make_float4(abspow(a.x, sg.p), abspow(a.y, sg.p), abspow(a.z, sg.p), abspow(a.w, sg.p)),
-                          W + k * Npad);
-            }
-            break;
-          case OP_SGNPOW:
-            for (int k = kb; k < sg.k1; k += KS) {
-              const float4 a = rows(terms[k].i);
-              fma_row<NT>(acc,
-                          make_float4(copysignf(abspow(a.x, sg.p), a.x), copysignf(abspow(a.y, sg.p), a.y),
-                                      copysignf(abspow(a.z, sg.p), a.z), copysignf(abspow(a.w, sg.p), a.w)),
-                          W + k * Npad);
-            }
-            break;
-          case OP_MUL3:
-            for (int k = kb; k < sg.k1; k += KS) {
-              const Term16 t = terms[k];
-              const float4 a = rows(t.i), b = rows(t.j), c = rows(t.k);
-              fma_row<NT>(acc, make_float4(a.x * b.x * c.x, a.y * b.y * c.y, a.z * b.z * c.z, a.w * b.w * c.w),
-                          W + k * Npad);
-            }
-            break;
-          case OP_ABS:
-            for (int k = kb; k < sg.k1; k += KS) {
-              const float4 a = rows(terms[k].i);
-              fma_row<NT>(acc, make_float4(fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w)), W + k * Npad);
-            }
-            break;
-          case OP_CLIP:
-            for (int k = kb; k < sg.k1; k += KS) {
-              const float4 a = rows(terms[k].i);
-              fma_row<NT>(acc, clamp4(a, -sg.p, sg.p), W + k * Npad);
-            }
-            break;
-          default:
-            break;
+            fma_row<NT, SW>(acc, a, w);
+          }
         }
       }
     }
 
-    Epilogue epi{op, ps, params + ps.b_off, xout, srow, tile, nvalid, col0, lane};
-    if (KS == 1) {
-      if (active) {
-#pragma unroll
-        for (int q = 0; q < NT / 2; ++q) {
-          const float2 y0 = unpack2(acc[0][q]), y1 = unpack2(acc[1][q]), y2 = unpack2(acc[2][q]), y3 = unpack2(acc[3][q]);
-          epi(n0 + 2 * q, make_float4(y0.x, y1.x, y2.x, y3.x));
-          epi(n0 + 2 * q + 1, make_float4(y0.y, y1.y, y2.y, y3.y));
-        }
-      }
-    } else {
-      // K-split: pairwise tree over the KS warps of a group (consecutive warps).  In every round the
-      // upper half parks its partial sums in shared memory and the lower half adds them, so the
-      // scratch area holds at most WARPS / 2 register tiles.
-      const int grp_slot0 = (warp / KS) * (KS >> 1);   // first scratch slot of this warp's K-split group
+    // ---- K-split: pairwise tree over the KS warps of a group (consecutive warps).  In every round the
+    // upper half parks its partial sums in shared memory and the lower half adds them, so the scratch
+    // area holds at most WARPS / 2 register tiles.
+    if (KS > 1) {
+      const int grp_slot0 = (warp / KS) * (KS >> 1);
       for (int stride = KS >> 1; stride >= 1; stride >>= 1) {
-        // round: parts [stride, 2*stride) park their sums, parts [0, stride) add them
         if (active && ks >= stride && ks < 2 * stride) {
-          float4* slot4 = reinterpret_cast<float4*>(scratch) + size_t(grp_slot0 + ks - stride) * NT * (TILE / 4) + lane;
+          float4* slot4 = reinterpret_cast<float4*>(scratch) + size_t(grp_slot0 + ks - stride) * SW * NT * (TILE / 4) + lane;
 #pragma unroll
-          for (int q = 0; q < NT / 2; ++q) {
-            const float2 y0 = unpack2(acc[0][q]), y1 = unpack2(acc[1][q]), y2 = unpack2(acc[2][q]), y3 = unpack2(acc[3][q]);
-            slot4[(2 * q) * (TILE / 4)] = make_float4(y0.x, y1.x, y2.x, y3.x);
-            slot4[(2 * q + 1) * (TILE / 4)] = make_float4(y0.y, y1.y, y2.y, y3.y);
-          }
+          for (int s = 0; s < SW; ++s)
+#pragma unroll
+            for (int q = 0; q < NT / 2; ++q) {
+              const float2 y0 = unpack2(acc[s][0][q]), y1 = unpack2(acc[s][1][q]), y2 = unpack2(acc[s][2][q]), y3 = unpack2(acc[s][3][q]);
+              slot4[(s * NT + 2 * q) * (TILE / 4)] = make_float4(y0.x, y1.x, y2.x, y3.x);
+              slot4[(s * NT + 2 * q + 1) * (TILE / 4)] = make_float4(y0.y, y1.y, y2.y, y3.y);
+            }
         }
         __syncthreads();
         if (active && ks < stride) {
-          const float4* part = reinterpret_cast<const float4*>(scratch) + size_t(grp_slot0 + ks) * NT * (TILE / 4) + lane;
+          const float4* part = reinterpret_cast<const float4*>(scratch) + size_t(grp_slot0 + ks) * SW * NT * (TILE / 4) + lane;
 #pragma unroll
-          for (int q = 0; q < NT / 2; ++q) {
-            const float4 u0 = part[(2 * q) * (TILE / 4)], u1 = part[(2 * q + 1) * (TILE / 4)];
-            float2 y0 = unpack2(acc[0][q]), y1 = unpack2(acc[1][q]), y2 = unpack2(acc[2][q]), y3 = unpack2(acc[3][q]);
-            y0.x += u0.x; y1.x += u0.y; y2.x += u0.z; y3.x += u0.w;
-            y0.y += u1.x; y1.y += u1.y; y2.y += u1.z; y3.y += u1.w;
-            acc[0][q] = pack2(y0); acc[1][q] = pack2(y1); acc[2][q] = pack2(y2); acc[3][q] = pack2(y3);
-          }
+          for (int s = 0; s < SW; ++s)
+#pragma unroll
+            for (int q = 0; q < NT / 2; ++q) {
+              const float4 u0 = part[(s * NT + 2 * q) * (TILE / 4)], u1 = part[(s * NT + 2 * q + 1) * (TILE / 4)];
+              float2 y0 = unpack2(acc[s][0][q]), y1 = unpack2(acc[s][1][q]), y2 = unpack2(acc[s][2][q]), y3 = unpack2(acc[s][3][q]);
+              y0.x += u0.x; y1.x += u0.y; y2.x += u0.z; y3.x += u0.w;
+              y0.y += u1.x; y1.y += u1.y; y2.y += u1.z; y3.y += u1.w;
+              acc[s][0][q] = pack2(y0); acc[s][1][q] = pack2(y1); acc[s][2][q] = pack2(y2); acc[s][3][q] = pack2(y3);
+            }
         }
         __syncthreads();   // scratch slots are reused by the next round / pass
       }
-      if (active && ks == 0) {
+    }
+    if (active && ks == 0) {
 #pragma unroll
-        for (int q = 0; q < NT / 2; ++q) {
-          const float2 y0 = unpack2(acc[0][q]), y1 = unpack2(acc[1][q]), y2 = unpack2(acc[2][q]), y3 = unpack2(acc[3][q]);
-          epi(n0 + 2 * q, make_float4(y0.x, y1.x, y2.x, y3.x));
-          epi(n0 + 2 * q + 1, make_float4(y0.y, y1.y, y2.y, y3.y));
+      for (int s = 0; s < SW; ++s) {
+        const int slot = slot0 + s;
+        const int64_t tile = tile0 + slot;
+        if (slot < op.twc && tile < ntiles) {
+          Epilogue epi{op, ps, params + ps.b_off, xout,
+                       reinterpret_cast<float*>(smem + op.sm_srows) + size_t(slot) * op.n_rows * TILE, tile, nvalid, col0, lane};
+#pragma unroll
+          for (int q = 0; q < NT / 2; ++q) {
+            const float2 y0 = unpack2(acc[s][0][q]), y1 = unpack2(acc[s][1][q]), y2 = unpack2(acc[s][2][q]), y3 = unpack2(acc[s][3][q]);
+            epi(n0 + 2 * q, make_float4(y0.x, y1.x, y2.x, y3.x));
+            epi(n0 + 2 * q + 1, make_float4(y0.y, y1.y, y2.y, y3.y));
+          }
         }
       }
     }
   }
 }
 
-// NTMAX bounds the register tile compiled in: 16 (NT 8/16) keeps 2 CTAs per SM, 32 adds NT 24/32.
+// NTMAX bounds the register tile compiled in: 16 (<= 64 accumulator registers) keeps 2 CTAs per SM,
+// 32 adds the 128-register tiles (NT 24 / 32, or NT 16 over two tile slots).
 template <typename IN_T, int NTMAX>
 __global__ void __launch_bounds__(THREADS, (NTMAX <= 16 ? 2 : 1))
     layer_kernel(const OpDev op, const IN_T* __restrict__ xin, float* __restrict__ xout, int64_t ntiles) {
@@ -384,11 +531,14 @@ __global__ void __launch_bounds__(THREADS, (NTMAX <= 16 ? 2 : 1))
 #pragma unroll 1
     for (int p = 0; p < op.n_passes; ++p) {
       const PassDev& ps = op.pass[p];
-      switch (ps.NT) {
-        case 8: run_pass<IN_T, 8>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
-        case 16: run_pass<IN_T, 16>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
-        case 24: if constexpr (NTMAX >= 32) run_pass<IN_T, 24>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
-        case 32: if constexpr (NTMAX >= 32) run_pass<IN_T, 32>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+      const int code = ps.NT * 4 + ps.SW;
+      switch (code) {
+        case 8 * 4 + 1: run_pass<IN_T, 8, 1>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+        case 16 * 4 + 1: run_pass<IN_T, 16, 1>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+        case 8 * 4 + 2: run_pass<IN_T, 8, 2>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+        case 16 * 4 + 2: if constexpr (NTMAX >= 32) run_pass<IN_T, 16, 2>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+        case 24 * 4 + 1: if constexpr (NTMAX >= 32) run_pass<IN_T, 24, 1>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+        case 32 * 4 + 1: if constexpr (NTMAX >= 32) run_pass<IN_T, 32, 1>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
         default: break;
       }
       __syncthreads();   // shared rows of this pass visible; stage fully consumed after the last pass

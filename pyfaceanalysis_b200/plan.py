@@ -508,16 +508,27 @@ def _op_smem(op, twc, el=4, stages=1):
     def up(x):
         return (x + 127) // 128 * 128
     n_terms = sum(ps["K"] for ps in op.passes)
-    scratch = max([(WARPS // 2) * ps["NT"] * TILE * 4 for ps in op.passes if _pass_split(ps, twc)[1] > 1] + [0])
+    scratch = 0
+    for ps in op.passes:
+        sw, tw, ks = _pass_split(ps, twc)
+        if ks > 1:
+            scratch = max(scratch, (WARPS // 2) * sw * ps["NT"] * TILE * 4)
     raw = op.d_in * TILE * el
     stage = up(twc * raw + op.param_floats * 4)
     return 128 + up(n_terms * 8) + up(twc * op.n_rows * TILE * 4) + up(scratch) + stages * stage
 
 
 def _pass_split(ps, twc):
-    """(TW, KS): tile slots processed concurrently and K-split so that TW * NTL * KS == WARPS."""
-    tw = min(twc, WARPS // ps["NTL"])
-    return tw, WARPS // (ps["NTL"] * tw)
+    """(SW, TW, KS): tile slots per warp, slot groups processed concurrently, K-split, with
+    TW * NTL * KS == WARPS.  Two slots per warp (a 8 windows x NT register tile) halve the weight reads per
+    FMA; they are used whenever the accumulators still fit (NT <= 16)."""
+    sw = 2 if (ps["NT"] <= 16 and twc >= 2 and TWO_SLOTS) else 1
+    tw = max(1, min(twc // sw, WARPS // ps["NTL"]))
+    return sw, tw, WARPS // (ps["NTL"] * tw)
+
+
+TWO_SLOTS = True
+FOLD_MEANS = True
 
 
 def _decompose(op):
@@ -530,16 +541,20 @@ def _decompose(op):
         ps["w_off"] = off
         off += ps["K"] * ps["Npad"]
     op.param_floats = -(-off // 4) * 4
-    fits = [t for t in (8, 4, 2, 1) if _op_smem(op, t) <= SMEM_TARGET]
-    if fits:
-        op.twc = fits[0]
-    else:
-        fits = [t for t in (8, 4, 2, 1) if _op_smem(op, t) <= SMEM_LIMIT]
-        if not fits:
-            raise UnsupportedFlow("a receptive field of %d inputs does not fit in shared memory" % op.d_in)
-        op.twc = fits[0]
+    # enough slots that no pass needs a K-split, then as many as shared memory allows
+    want = 1
     for ps in op.passes:
-        ps["TW"], ps["KS"] = _pass_split(ps, op.twc)
+        sw = 2 if (ps["NT"] <= 16 and TWO_SLOTS) else 1
+        want = max(want, min(16, sw * (WARPS // ps["NTL"])))
+    wide = any(ps["NT"] > 16 or (ps["NT"] == 16 and TWO_SLOTS) for ps in op.passes)
+    budget = SMEM_LIMIT if wide else SMEM_TARGET
+    cands = [t for t in (16, 8, 4, 2, 1) if t <= want]
+    fits = [t for t in cands if _op_smem(op, t) <= budget] or [t for t in cands if _op_smem(op, t) <= SMEM_LIMIT]
+    if not fits:
+        raise UnsupportedFlow("a receptive field of %d inputs does not fit in shared memory" % op.d_in)
+    op.twc = fits[0]
+    for ps in op.passes:
+        ps["SW"], ps["TW"], ps["KS"] = _pass_split(ps, op.twc)
     op.npc = max(1, min(8, op.n_nodes // 32))
     runs = [_gather_runs(g) for g in op.gather]
     op.n_runs = max(len(r) for r in runs)
@@ -549,17 +564,36 @@ def _decompose(op):
             op.runs[nd, r] = (i0, f0, ln, 0)
 
 
-def _segments(terms):
-    """Runs of consecutive terms sharing (op, exponent): list of (op, k0, k1, p)."""
+def _segments(terms, d_in):
+    """Runs of consecutive terms sharing (op, exponent, operand kind): list of
+    (op, k0, k1, p, kind, ibase).  kind 0: operands are receptive-field rows, 1: shared rows of an
+    earlier pass, 2: mixed.  ibase >= 0 when operand i advances by one row per term (no table lookup)."""
+    n = len(terms)
+    ops = terms["op"]
+    no_p = (ex.OP_ID, ex.OP_MUL, ex.OP_MUL3, ex.OP_ABS)
+
+    def kind_of(k):
+        rows = [int(terms["i"][k])]
+        if ops[k] in (ex.OP_MUL, ex.OP_MUL3):
+            rows.append(int(terms["j"][k]))
+        if ops[k] == ex.OP_MUL3:
+            rows.append(int(terms["p"][k]))
+        lo = all(r < d_in for r in rows)
+        hi = all(r >= d_in for r in rows)
+        return 0 if lo else (1 if hi else 2)
+
+    kinds = [kind_of(k) for k in range(n)]
     segs = []
     k0 = 0
-    for k in range(1, len(terms) + 1):
-        same = k < len(terms) and terms["op"][k] == terms["op"][k0] and (
-            terms["op"][k] in (ex.OP_ID, ex.OP_MUL, ex.OP_MUL3, ex.OP_ABS) or terms["p"][k] == terms["p"][k0])
+    for k in range(1, n + 1):
+        same = (k < n and ops[k] == ops[k0] and kinds[k] == kinds[k0]
+                and (ops[k] in no_p or terms["p"][k] == terms["p"][k0]))
         if not same:
-            op_code = int(terms["op"][k0])
-            p = 0.0 if op_code in (ex.OP_ID, ex.OP_MUL, ex.OP_MUL3, ex.OP_ABS) else float(terms["p"][k0])
-            segs.append((op_code, k0, k, p))
+            op_code = int(ops[k0])
+            p = 0.0 if op_code in no_p else float(terms["p"][k0])
+            i = terms["i"][k0:k].astype(np.int64)
+            affine = bool(np.array_equal(i, i[0] + np.arange(k - k0)))
+            segs.append((op_code, k0, k, p, kinds[k0], int(i[0]) if affine else -1))
             k0 = k
     return segs
 
@@ -725,8 +759,22 @@ def serialize(spec):
         params[:, :op.d_in] = op.in_offset
         t16 = np.zeros((n_terms, 4), dtype=np.int16)
         t_off = 0
+        seg_lists = []
         for ps in op.passes:
-            params[:, ps["b_off"]:ps["b_off"] + ps["Npad"]] = ps["b"]
+            segs = _segments(ps["terms"], op.d_in)
+            bias = ps["b"].astype(np.float64).copy()
+            flagged = []
+            for (o, k0, k1, p, kind, ibase) in segs:
+                nomean = 0
+                if o == ex.OP_ID and kind == 0 and ibase >= 0 and FOLD_MEANS:
+                    # identity terms over the receptive field: x_mean goes into the bias (float64 here),
+                    # the kernel then feeds the raw rows to the FMAs
+                    m = op.in_offset[:, ibase:ibase + (k1 - k0)]                      # (n_w, len)
+                    bias -= np.einsum("wk,wkn->wn", m, ps["W"][:, k0:k1, :])
+                    nomean = 1
+                flagged.append((o, k0, k1, p, kind, ibase, nomean))
+            seg_lists.append(flagged)
+            params[:, ps["b_off"]:ps["b_off"] + ps["Npad"]] = bias
             params[:, ps["w_off"]:ps["w_off"] + ps["K"] * ps["Npad"]] = ps["W"].reshape(n_w, -1)
             t = ps["terms"]
             t16[t_off:t_off + ps["K"], 0] = t["i"]
@@ -739,12 +787,12 @@ def serialize(spec):
             raise ValueError("non-finite flow parameters")
         out.append(_arr(params, np.float32))
         out.append(_arr(t16, np.int16))
-        for ps in op.passes:
-            segs = _segments(ps["terms"])
+        for ps, segs in zip(op.passes, seg_lists):
             out.append(struct.pack("<16q", ps["K"], ps["Npad"], ps["NT"], ps["NTL"], ps["KS"], ps["TW"], ps["dst"],
                                    ps["row0"], ps["w_off"], ps["b_off"], ps["term_off"], len(segs), ps["K_real"],
-                                   ps["N_real"], 0, 0))
-            sb = b"".join(struct.pack("<3if", o, k0, k1, p) for (o, k0, k1, p) in segs)
+                                   ps["N_real"], ps["SW"], 0))
+            sb = b"".join(struct.pack("<3if4i", o, k0, k1, p, kind, ibase, nomean, 0)
+                          for (o, k0, k1, p, kind, ibase, nomean) in segs)
             out.append(_pad16(sb))
             out.append(_arr(ps["n_valid"], np.int32))
             out.append(_arr(ps["col_off"], np.int32))
@@ -755,7 +803,7 @@ def describe(spec):
     lines = ["plan: %d -> %d, %d ops, %.3f MFLOP/window algorithmic, %.3f executed"
              % (spec.input_dim, spec.output_dim, len(spec.ops), spec.alg_flops / 1e6, spec.exe_flops / 1e6)]
     for k, op in enumerate(spec.ops):
-        ps = ", ".join("K%d->N%d(%dx%d ks%d tw%d)" % (p["K_real"], p["N_real"], p["NT"], p["NTL"], p["KS"], p["TW"])
+        ps = ", ".join("K%d->N%d(%dx%d sw%d ks%d tw%d)" % (p["K_real"], p["N_real"], p["NT"], p["NTL"], p["SW"], p["KS"], p["TW"])
                        for p in op.passes)
         lines.append("  op%-2d nodes=%-4d d_in=%-4d out=%-5d %s %s [%s] twc=%d npc=%d runs=%d rows=%d smem=%dK"
                      % (k, op.n_nodes, op.d_in, op.out_dim, "clone" if op.shared else "layer", op.mode, ps,
