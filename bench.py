@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--windows", type=int, default=N_WINDOWS, help="windows per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--front-chunk", type=int, default=0, help="windows per front-segment chunk (0 = library default)")
+    ap.add_argument("--back-chunk", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
@@ -211,6 +213,8 @@ def main():
 
     flow = synthetic.cached_flow(FLOW_SPEC, seed=0)
     g = GpuFlow(flow, device=local_rank)
+    if args.front_chunk or args.back_chunk:
+        g.set_chunks(front=args.front_chunk, back=args.back_chunk)
     n = args.windows
     F = g.output_dim
 

@@ -118,7 +118,9 @@ struct hgsfa_plan_s {
   std::vector<OpHost> ops;
   DevBuf params;                     // the whole blob: every plan array is an offset into it
   DevBuf tin, front[2], mid, back[2], stage_x[2], stage_y[2];
-  int64_t front_chunk = 16384, back_chunk = 262144;
+  // measured on B200 (profiles/README_r01.md): launches of >= 128 Ki windows hide the wave tail of the
+  // one-CTA-per-SM layer kernels; smaller chunks only pay when the batch itself is small
+  int64_t front_chunk = 131072, back_chunk = 262144;
   int split = 0;                     // ops [0, split) run per front chunk, [split, n) per back chunk
   int64_t launches = 0;
   double last_ms = 0.0;
@@ -271,11 +273,13 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       if (!cur.ok) break;
       int kcov = 0;
       for (int sgi = 0; sgi < dp.n_seg; ++sgi) {
-        if (segs[sgi].op < 0 || segs[sgi].op > OP_CLIP || segs[sgi].k0 != kcov || segs[sgi].k1 < segs[sgi].k0 ||
+        if (segs[sgi].op < 0 || segs[sgi].op > OP_ID_POW || segs[sgi].k0 != kcov || segs[sgi].k1 < segs[sgi].k0 ||
             segs[sgi].kind < 0 || segs[sgi].kind > 2 ||
-            (segs[sgi].ibase >= 0 && segs[sgi].ibase + (segs[sgi].k1 - segs[sgi].k0) > d.d_in + d.n_rows) ||
-            (segs[sgi].ibase >= 0 && segs[sgi].kind == 0 && segs[sgi].ibase + (segs[sgi].k1 - segs[sgi].k0) > d.d_in) ||
-            (segs[sgi].ibase >= 0 && segs[sgi].kind == 1 && segs[sgi].ibase < d.d_in))
+            (segs[sgi].op != OP_ID_POW && segs[sgi].ibase >= 0 && segs[sgi].ibase + (segs[sgi].k1 - segs[sgi].k0) > d.d_in + d.n_rows) ||
+            (segs[sgi].op != OP_ID_POW && segs[sgi].ibase >= 0 && segs[sgi].kind == 0 && segs[sgi].ibase + (segs[sgi].k1 - segs[sgi].k0) > d.d_in) ||
+            (segs[sgi].ibase >= 0 && segs[sgi].kind == 1 && segs[sgi].ibase < d.d_in) ||
+            (segs[sgi].op == OP_ID_POW && (segs[sgi].kind != 0 || segs[sgi].ibase < 0 || ((segs[sgi].k1 - segs[sgi].k0) & 1) ||
+                                           segs[sgi].ibase + (segs[sgi].k1 - segs[sgi].k0) / 2 > d.d_in)))
           return plan_fail(pl, "op %lld pass %d: bad term segment %d", (long long)o, p, sgi);
         kcov = segs[sgi].k1;
       }

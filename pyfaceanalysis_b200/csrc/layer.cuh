@@ -32,7 +32,8 @@ constexpr int MAX_PASSES = 4;
 constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
 
-enum TermOp { OP_ID = 0, OP_MUL = 1, OP_ABSPOW = 2, OP_SGNPOW = 3, OP_MUL3 = 4, OP_ABS = 5, OP_CLIP = 6 };
+enum TermOp { OP_ID = 0, OP_MUL = 1, OP_ABSPOW = 2, OP_SGNPOW = 3, OP_MUL3 = 4, OP_ABS = 5, OP_CLIP = 6,
+              OP_ID_POW = 7 /* segment-only: identity rows followed by |x|^p rows over the same inputs */ };
 enum { DST_GLOBAL = 1, DST_ROWS = 2 };
 
 struct Term16 { int16_t i, j, k, pad; };        // source rows of one expansion term
@@ -196,7 +197,7 @@ __device__ __forceinline__ float4 mul4(const float4 a, const float4 b) {
 //   (C) runs the FMAs of row it,
 // so every dependent instruction finds its inputs at least one full row of FMAs old.
 // ------------------------------------------------------------------------------------------------
-enum SegMode { M_ID_NOMEAN = 0, M_ID_MEAN = 1, M_ID_SROW = 2, M_POW = 3, M_MUL = 4 };
+enum SegMode { M_ID_NOMEAN = 0, M_ID_MEAN = 1, M_ID_SROW = 2, M_POW = 3, M_MUL = 4, M_ID_POW = 5 };
 
 template <int NT>
 struct WReg { ulonglong2 q[NT / 4]; };
@@ -223,8 +224,18 @@ __device__ __forceinline__ void fma_regs(unsigned long long (&acc)[SW][4][NT / 2
   }
 }
 
+// Base pointers of the SW tile slots a warp works on (already offset to this lane's 4 windows); slot s
+// lives raw_stride / srow_stride elements after slot 0.
+template <typename IN_T>
+struct SlotPtrs {
+  const IN_T* raw0;
+  const float* srow0;
+  const float* mean;
+  int raw_stride, srow_stride;
+};
+
 // un-converted operands of one row for SW slots
-template <typename IN_T, int SW, int MODE>
+template <typename IN_T, int SW>
 struct RawRow {
   float4 f[SW];     // float sources (f32 rows / shared rows), or first operand of a product
   float4 g[SW];     // second operand of a product
@@ -234,31 +245,39 @@ struct RawRow {
 };
 
 template <typename IN_T, int SW, int MODE>
-__device__ __forceinline__ void load_raw(RawRow<IN_T, SW, MODE>& r, const Rows<IN_T> (&rows)[SW], int i, int j) {
+__device__ __forceinline__ void load_raw(RawRow<IN_T, SW>& r, const SlotPtrs<IN_T>& sp, int i, int j) {
+  if (MODE == M_ID_SROW) {
+    const float* q = sp.srow0 + i * TILE;
+#pragma unroll
+    for (int s = 0; s < SW; ++s) r.f[s] = *reinterpret_cast<const float4*>(q + s * sp.srow_stride);
+    return;
+  }
+  const IN_T* q = sp.raw0 + i * TILE;
+  const IN_T* q2 = sp.raw0 + j * TILE;
 #pragma unroll
   for (int s = 0; s < SW; ++s) {
-    if (MODE == M_ID_SROW) {
-      r.f[s] = *reinterpret_cast<const float4*>(rows[s].srowp + size_t(i) * TILE);
-    } else if (sizeof(IN_T) == 1) {
-      r.u[s] = *reinterpret_cast<const uint32_t*>(rows[s].rawp + size_t(i) * TILE);
-      if (MODE == M_MUL) r.v[s] = *reinterpret_cast<const uint32_t*>(rows[s].rawp + size_t(j) * TILE);
+    if (sizeof(IN_T) == 1) {
+      r.u[s] = *reinterpret_cast<const uint32_t*>(q + s * sp.raw_stride);
+      if (MODE == M_MUL) r.v[s] = *reinterpret_cast<const uint32_t*>(q2 + s * sp.raw_stride);
     } else {
-      r.f[s] = *reinterpret_cast<const float4*>(rows[s].rawp + size_t(i) * TILE);
-      if (MODE == M_MUL) r.g[s] = *reinterpret_cast<const float4*>(rows[s].rawp + size_t(j) * TILE);
+      r.f[s] = *reinterpret_cast<const float4*>(q + s * sp.raw_stride);
+      if (MODE == M_MUL) r.g[s] = *reinterpret_cast<const float4*>(q2 + s * sp.raw_stride);
     }
   }
-  if (MODE == M_ID_MEAN || MODE == M_POW || MODE == M_MUL) r.m = rows[0].mean[i];
-  if (MODE == M_MUL) r.m2 = rows[0].mean[j];
+  if (MODE != M_ID_NOMEAN) r.m = sp.mean[i];
+  if (MODE == M_MUL) r.m2 = sp.mean[j];
 }
 
 __device__ __forceinline__ float4 sub4(float4 v, float m) { return make_float4(v.x - m, v.y - m, v.z - m, v.w - m); }
 
+// a = operand of the (first) FMA block; b = |x|^p operand of the second block (M_ID_POW only)
 template <typename IN_T, int SW, int MODE>
-__device__ __forceinline__ void convert_raw(float4 (&a)[SW], const RawRow<IN_T, SW, MODE>& r, float p) {
+__device__ __forceinline__ void convert_raw(float4 (&a)[SW], float4 (&b)[SW], const RawRow<IN_T, SW>& r, float p) {
 #pragma unroll
   for (int s = 0; s < SW; ++s) {
     float4 x = (MODE != M_ID_SROW && sizeof(IN_T) == 1) ? u8x4_to_float4(r.u[s]) : r.f[s];
-    if (MODE == M_ID_MEAN || MODE == M_POW || MODE == M_MUL) x = sub4(x, r.m);
+    if (MODE == M_ID_MEAN || MODE == M_POW || MODE == M_MUL || MODE == M_ID_POW) x = sub4(x, r.m);
+    if (MODE == M_ID_POW) b[s] = pow4(x, p);
     if (MODE == M_POW) x = pow4(x, p);
     if (MODE == M_MUL) {
       float4 y = (sizeof(IN_T) == 1) ? u8x4_to_float4(r.v[s]) : r.g[s];
@@ -268,45 +287,71 @@ __device__ __forceinline__ void convert_raw(float4 (&a)[SW], const RawRow<IN_T, 
   }
 }
 
-// rows i0, i0+istep, ... (n of them); weights w0, w0+wstep, ...; for M_MUL the operand rows come from
-// the term table (terms[0], terms[tstep], ...)
+// Rows i0, i0+istep, ... (n of them), weight rows w0, w0+wstep, ...  M_MUL takes its operand rows from the
+// term table (terms[0], terms[tstep], ...).  M_ID_POW feeds every row to two weight rows: w0 + it*wstep
+// (identity) and w0 + pow_off + it*wstep (|x|^p) -- the [identity, |x|^0.8] expansion reads and centres
+// each input once.  Indices are advanced with clamped additions: the pipeline fetches up to two rows
+// past the end, which must stay inside the segment.
 template <typename IN_T, int NT, int SW, int MODE>
-__device__ __forceinline__ void seg_pipeline(unsigned long long (&acc)[SW][4][NT / 2], const Rows<IN_T> (&rows)[SW],
-                                             const float* w0, int wstep, int i0, int istep, int n, float p,
+__device__ __forceinline__ void seg_pipeline(unsigned long long (&acc)[SW][4][NT / 2], const SlotPtrs<IN_T>& sp,
+                                             const float* w0, int wstep, int pow_off, int i0, int istep, int n, float p,
                                              const Term16* terms, int tstep) {
   if (n <= 0) return;
-  RawRow<IN_T, SW, MODE> R[2];
-  float4 a[2][SW];
+  RawRow<IN_T, SW> R[2];
+  float4 a[2][SW], b[2][SW];
   WReg<NT> w[2];
-  auto row_ij = [&](int it, int& i, int& j) {
-    const int c = min(it, n - 1);          // clamped: the pipeline over-fetches up to two rows
+  WReg<NT> wp;
+  const int i_last = i0 + (n - 1) * istep;
+  const float* w_last = w0 + (n - 1) * wstep;
+  const Term16* t_last = terms + (n - 1) * tstep;
+  int i_ld = i0;                 // row whose raw operands are loaded next
+  const Term16* t_ld = terms;
+  const float* w_ld = w0;        // weight row loaded next
+  auto load_next_raw = [&](RawRow<IN_T, SW>& dst) {
     if (MODE == M_MUL) {
-      const Term16 t = terms[c * tstep];
-      i = t.i; j = t.j;
+      const Term16 t = *t_ld;
+      load_raw<IN_T, SW, MODE>(dst, sp, t.i, t.j);
+      t_ld = (t_ld + tstep <= t_last) ? t_ld + tstep : t_last;
     } else {
-      i = i0 + c * istep; j = 0;
+      load_raw<IN_T, SW, MODE>(dst, sp, i_ld, 0);
+      i_ld = min(i_ld + istep, i_last);
     }
   };
-  int i, j;
-  row_ij(0, i, j); load_raw<IN_T, SW, MODE>(R[0], rows, i, j);
-  row_ij(1, i, j); load_raw<IN_T, SW, MODE>(R[1], rows, i, j);
-  load_w<NT>(w[0], w0);
-  convert_raw<IN_T, SW, MODE>(a[0], R[0], p);
+  auto next_w = [&]() {
+    const float* r = w_ld;
+    w_ld = (w_ld + wstep <= w_last) ? w_ld + wstep : w_last;
+    return r;
+  };
+  load_next_raw(R[0]);
+  load_next_raw(R[1]);
+  const float* w_cur = next_w();
+  load_w<NT>(w[0], w_cur);
+  convert_raw<IN_T, SW, MODE>(a[0], b[0], R[0], p);
   int it = 0;
 #pragma unroll 1
   for (; it + 1 < n; it += 2) {
-    // step it (parity 0)
-    row_ij(it + 2, i, j); load_raw<IN_T, SW, MODE>(R[0], rows, i, j);
-    load_w<NT>(w[1], w0 + min(it + 1, n - 1) * wstep);
-    convert_raw<IN_T, SW, MODE>(a[1], R[1], p);
+    // ---- step it: buffers 0 hold the current row
+    if (MODE == M_ID_POW) load_w<NT>(wp, w_cur + pow_off);
+    load_next_raw(R[0]);
+    w_cur = next_w();
+    load_w<NT>(w[1], w_cur);
     fma_regs<NT, SW>(acc, a[0], w[0]);
-    // step it + 1 (parity 1)
-    row_ij(it + 3, i, j); load_raw<IN_T, SW, MODE>(R[1], rows, i, j);
-    load_w<NT>(w[0], w0 + min(it + 2, n - 1) * wstep);
-    convert_raw<IN_T, SW, MODE>(a[0], R[0], p);
+    convert_raw<IN_T, SW, MODE>(a[1], b[1], R[1], p);
+    if (MODE == M_ID_POW) fma_regs<NT, SW>(acc, b[0], wp);
+    // ---- step it + 1: buffers 1
+    if (MODE == M_ID_POW) load_w<NT>(wp, w_cur + pow_off);
+    load_next_raw(R[1]);
+    w_cur = next_w();
+    load_w<NT>(w[0], w_cur);
     fma_regs<NT, SW>(acc, a[1], w[1]);
+    convert_raw<IN_T, SW, MODE>(a[0], b[0], R[0], p);
+    if (MODE == M_ID_POW) fma_regs<NT, SW>(acc, b[1], wp);
   }
-  if (it < n) fma_regs<NT, SW>(acc, a[0], w[0]);
+  if (it < n) {
+    if (MODE == M_ID_POW) load_w<NT>(wp, w_cur + pow_off);
+    fma_regs<NT, SW>(acc, a[0], w[0]);
+    if (MODE == M_ID_POW) fma_regs<NT, SW>(acc, b[0], wp);
+  }
 }
 
 // bias + saturation + store of 4 windows x 1 column
@@ -357,32 +402,46 @@ __device__ __forceinline__ void run_pass(const OpDev& op, const PassDev& ps, int
         for (int q = 0; q < NT / 2; ++q) acc[s][r][q] = 0ull;
 
     if (active) {
-      Rows<IN_T> rows[SW];
+      // a slot past the end of the batch holds stale shared memory: computed, never stored
+      const int d_in = op.d_in, n_rows = op.n_rows;
+      SlotPtrs<IN_T> sp;
+      sp.raw0 = reinterpret_cast<const IN_T*>(stage + size_t(slot0) * op.sm_raw_bytes) + lane * 4;
+      sp.srow0 = reinterpret_cast<const float*>(smem + op.sm_srows) + size_t(slot0) * n_rows * TILE + lane * 4;
+      sp.mean = params;
+      sp.raw_stride = (slot0 + 1 < op.twc) ? op.sm_raw_bytes / int(sizeof(IN_T)) : 0;
+      sp.srow_stride = (slot0 + 1 < op.twc) ? n_rows * TILE : 0;
+      Rows<IN_T> rows[SW];   // generic (rare) path
 #pragma unroll
       for (int s = 0; s < SW; ++s) {
-        // a slot past the end of the batch holds stale shared memory: computed, never stored
-        const int slot = min(slot0 + s, op.twc - 1);
-        rows[s].rawp = reinterpret_cast<const IN_T*>(stage + size_t(slot) * op.sm_raw_bytes) + lane * 4;
-        rows[s].srowp = reinterpret_cast<const float*>(smem + op.sm_srows) + size_t(slot) * op.n_rows * TILE + lane * 4;
+        rows[s].rawp = sp.raw0 + s * sp.raw_stride;
+        rows[s].srowp = sp.srow0 + s * sp.srow_stride;
         rows[s].mean = params;
-        rows[s].d_in = op.d_in;
+        rows[s].d_in = d_in;
       }
-      for (int sgi = 0; sgi < ps.n_seg; ++sgi) {
-        const Seg sg = ps.segs[sgi];
+      const int n_seg = ps.n_seg;
+      const Seg* segs = ps.segs;
+      for (int sgi = 0; sgi < n_seg; ++sgi) {
+        const Seg sg = segs[sgi];
         const int kb = sg.k0 + ks;
         const float* w = W + kb * Npad;
         float4 a[SW];
-        const int n_rows_here = (sg.k1 - kb + KS - 1) / KS;   // rows of this segment owned by this K-split part
+        if (sg.op == OP_ID_POW) {
+          const int half = (sg.k1 - sg.k0) >> 1;          // identity rows [k0, k0+half), |x|^p rows after them
+          const int n_here = (sg.k0 + half - kb + KS - 1) / KS;
+          seg_pipeline<IN_T, NT, SW, M_ID_POW>(acc, sp, w, wstep, half * Npad, sg.ibase + ks, KS, n_here, sg.p, terms, 0);
+          continue;
+        }
+        const int n_here = (sg.k1 - kb + KS - 1) / KS;   // rows of this segment owned by this K-split part
         if (sg.op == OP_ID && sg.kind == 0 && sg.ibase >= 0 && sg.nomean) {
-          seg_pipeline<IN_T, NT, SW, M_ID_NOMEAN>(acc, rows, w, wstep, sg.ibase + ks, KS, n_rows_here, 0.f, terms, 0);
+          seg_pipeline<IN_T, NT, SW, M_ID_NOMEAN>(acc, sp, w, wstep, 0, sg.ibase + ks, KS, n_here, 0.f, terms, 0);
         } else if (sg.op == OP_ID && sg.kind == 0 && sg.ibase >= 0) {
-          seg_pipeline<IN_T, NT, SW, M_ID_MEAN>(acc, rows, w, wstep, sg.ibase + ks, KS, n_rows_here, 0.f, terms, 0);
+          seg_pipeline<IN_T, NT, SW, M_ID_MEAN>(acc, sp, w, wstep, 0, sg.ibase + ks, KS, n_here, 0.f, terms, 0);
         } else if (sg.op == OP_ID && sg.kind == 1 && sg.ibase >= 0) {
-          seg_pipeline<IN_T, NT, SW, M_ID_SROW>(acc, rows, w, wstep, sg.ibase - op.d_in + ks, KS, n_rows_here, 0.f, terms, 0);
+          seg_pipeline<IN_T, NT, SW, M_ID_SROW>(acc, sp, w, wstep, 0, sg.ibase - d_in + ks, KS, n_here, 0.f, terms, 0);
         } else if (sg.op == OP_ABSPOW && sg.kind == 0 && sg.ibase >= 0) {
-          seg_pipeline<IN_T, NT, SW, M_POW>(acc, rows, w, wstep, sg.ibase + ks, KS, n_rows_here, sg.p, terms, 0);
+          seg_pipeline<IN_T, NT, SW, M_POW>(acc, sp, w, wstep, 0, sg.ibase + ks, KS, n_here, sg.p, terms, 0);
         } else if (sg.op == OP_MUL && sg.kind == 0) {
-          seg_pipeline<IN_T, NT, SW, M_MUL>(acc, rows, w, wstep, 0, 0, n_rows_here, 0.f, terms + kb, KS);
+          seg_pipeline<IN_T, NT, SW, M_MUL>(acc, sp, w, wstep, 0, 0, 0, n_here, 0.f, terms + kb, KS);
         } else {
           // everything else (rare): generic operand fetch, one term at a time
           for (int k = kb; k < sg.k1; k += KS, w += wstep) {

@@ -296,7 +296,9 @@ class _Lowerer(object):
         cost_fold = padded(D + len(missing), J + P) if J + P <= 256 else float("inf")
         mode = self.igsfa_mode
         if mode == "auto":
-            mode = "fold" if cost_fold <= 1.1 * cost_two else "two_pass"
+            # the single folded pass has no shared-row round trip, no second epilogue and no K-split
+            # reduction; measured on B200 it wins until it executes ~1.5x the flops of the two-pass form
+            mode = "fold" if cost_fold <= FOLD_BIAS * cost_two else "two_pass"
         if mode == "fold":
             Tf = np.concatenate([T, _identity_terms(missing)]) if missing else T
             Wf = np.zeros((len(Tf), J + P))
@@ -527,8 +529,11 @@ def _pass_split(ps, twc):
     return sw, tw, WARPS // (ps["NTL"] * tw)
 
 
-TWO_SLOTS = True
-FOLD_MEANS = True
+import os as _os
+
+# tuning switches (environment overrides are for experiments; defaults are what the measurements favour)
+TWO_SLOTS = _os.environ.get("HGSFA_TWO_SLOTS", "1") != "0"
+FOLD_MEANS = _os.environ.get("HGSFA_FOLD_MEANS", "1") != "0"
 
 
 def _decompose(op):
@@ -555,13 +560,39 @@ def _decompose(op):
     op.twc = fits[0]
     for ps in op.passes:
         ps["SW"], ps["TW"], ps["KS"] = _pass_split(ps, op.twc)
-    op.npc = max(1, min(8, op.n_nodes // 32))
+    op.npc = max(1, min(int(_os.environ.get("HGSFA_NPC", "8")), op.n_nodes // 32))
     runs = [_gather_runs(g) for g in op.gather]
     op.n_runs = max(len(r) for r in runs)
     op.runs = np.zeros((op.n_nodes, op.n_runs, 4), dtype=np.int32)
     for nd, rl in enumerate(runs):
         for r, (i0, f0, ln) in enumerate(rl):
             op.runs[nd, r] = (i0, f0, ln, 0)
+
+
+OP_ID_POW = 7   # segment-only op code (csrc/layer.cuh): identity rows followed by |x|^p rows of the same inputs
+
+
+def _fuse_id_pow(segs):
+    """[identity over rows R][|x|^p over the same rows R] -> one fused segment: the kernel reads and centres
+    every input once and feeds it to both weight rows."""
+    out = []
+    k = 0
+    while k < len(segs):
+        s0 = segs[k]
+        if (FUSE_ID_POW and k + 1 < len(segs) and s0[0] == ex.OP_ID and s0[4] == 0 and s0[5] >= 0):
+            s1 = segs[k + 1]
+            if (s1[0] == ex.OP_ABSPOW and s1[4] == 0 and s1[5] == s0[5] and s1[1] == s0[2]
+                    and s1[2] - s1[1] == s0[2] - s0[1]):
+                out.append((OP_ID_POW, s0[1], s1[2], s1[3], 0, s0[5]))
+                k += 2
+                continue
+        out.append(s0)
+        k += 1
+    return out
+
+
+FOLD_BIAS = float(_os.environ.get("HGSFA_FOLD_BIAS", "1.5"))
+FUSE_ID_POW = _os.environ.get("HGSFA_FUSE_ID_POW", "1") != "0"
 
 
 def _segments(terms, d_in):
@@ -619,6 +650,8 @@ class PlanSpec(object):
 
 def compile_flow(flow, input_dim=None, igsfa_mode="auto"):
     """Lower a flow (object with ``.flow`` or a sequence of nodes) to a :class:`PlanSpec`."""
+    if igsfa_mode == "auto":
+        igsfa_mode = _os.environ.get("HGSFA_IGSFA_MODE", "auto")
     nodes = flow_nodes(flow)
     if not nodes:
         raise UnsupportedFlow("empty flow")
@@ -761,7 +794,7 @@ def serialize(spec):
         t_off = 0
         seg_lists = []
         for ps in op.passes:
-            segs = _segments(ps["terms"], op.d_in)
+            segs = _fuse_id_pow(_segments(ps["terms"], op.d_in))
             bias = ps["b"].astype(np.float64).copy()
             flagged = []
             for (o, k0, k1, p, kind, ibase) in segs:
