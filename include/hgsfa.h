@@ -114,6 +114,15 @@ int hgsfa_crop_extent_device(const uint8_t* d_img, int H, int W, const double* d
                              const double* d_angles, int64_t n, int ow, int oh, int filter,
                              void* d_out, int out_dtype, int out_layout, void* stream);
 
+/* batch version: window w is extracted from image d_img_index[w]; d_img_ptrs[k] is the device address of
+ * image k (uint8, row-major, leading dimension = its width) and d_img_hw[2k], d_img_hw[2k+1] its height and
+ * width -- the windows of every image and scale of a detection batch in ONE launch
+ * (the reference loops over windows, FaceDetectUpdated.py:686 -> face_analysis.py:781-786). */
+int hgsfa_crop_extent_batch_device(const uint8_t* const* d_img_ptrs, const int32_t* d_img_hw,
+                                   const int32_t* d_img_index, const double* d_boxes,
+                                   const double* d_angles, int64_t n, int ow, int oh, int filter,
+                                   void* d_out, int out_dtype, int out_layout, void* stream);
+
 /* row-major <-> tiled conversion of a window matrix on the device (u8 or f32 elements) */
 int hgsfa_tile_windows_device(const void* d_src, int dtype, int64_t n, int64_t dim, int64_t ld,
                               void* d_dst_tiled, int dst_dtype, void* stream);
@@ -144,6 +153,34 @@ int hgsfa_gauss_regress(hgsfa_gauss_t h, const void* x, int x_dtype, int64_t n, 
 int hgsfa_gauss_regress_device(hgsfa_gauss_t h, const void* d_x, int x_dtype, int64_t n, int64_t ld,
                                const double* d_avg_labels, double* d_value, double* d_std,
                                int32_t* d_winner, double* d_probs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cascade controller on the device: replaces, for a batch of windows,
+ *   update_current_subimage_coordinates(network_type, coords, angles, reg_out, ...)  face_analysis.py:803-840
+ *   identify_patches_to_discard(network_type, ...)                                   face_analysis.py:842-887
+ *   the order-preserving compaction block                                            FaceDetectUpdated.py:739-759
+ *
+ * type: 0 Disc, 1 PosX, 2 PosY, 3 PAng, 4 Scale.  coords (n x 4) and angles (n) are updated in place,
+ * keep[i] = !new_wrong_images[i]; for Disc stages conf[i] = reg_out[i] (curr_confidence) when conf != NULL.
+ * orig_coords / orig_angles / patch_wh ([.][2] = patch_width, patch_height of the window's scale) are
+ * indexed through orig_index, like orig_subimage_coordinates[curr_orig_index] in the reference.
+ * params12 = {net_Dx, net_Dy, net_Dang, regression_width, regression_height, min_scale_radio,
+ *             max_scale_radio, tolerance_posxy, tolerance_scale, tolerance_angle, desired_sampling,
+ *             cut_off_face}.  float64 throughout, reference operation order, no FMA contraction.
+ * ---------------------------------------------------------------------------------------------- */
+int hgsfa_cascade_update_device(int type, double* d_coords, double* d_angles, const double* d_reg_out,
+                                const double* d_orig_coords, const double* d_orig_angles,
+                                const int32_t* d_orig_index, const double* d_patch_wh, int64_t n,
+                                const double* params12, uint8_t* d_keep, double* d_conf, void* stream);
+
+/* src_index[j] = index of the j-th kept element (ascending), *d_count = number kept (device int64).
+ * d_scratch: at least ceil(n / 1024) int32. */
+int hgsfa_compact_index_device(const uint8_t* d_keep, int64_t n, int32_t* d_src_index, int64_t* d_count,
+                               int32_t* d_scratch, int64_t scratch_ints, void* stream);
+
+/* dst[j] = src[index[j]] for rows of row_bytes bytes (multiple of 4): curr_x = curr_x[new_wrong_images == 0] */
+int hgsfa_gather_rows_device(const void* d_src, void* d_dst, const int32_t* d_index, int64_t n_out,
+                             int64_t row_bytes, void* stream);
 
 #ifdef __cplusplus
 }

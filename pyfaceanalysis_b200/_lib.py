@@ -36,11 +36,15 @@ SYMBOLS = [
     ("hgsfa_plan_set_chunks", _int, [_vp, _i64, _i64]),
     ("hgsfa_crop_extent", _int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int, _int, _vp, _int, _int, _vp]),
     ("hgsfa_crop_extent_device", _int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int, _int, _vp, _int, _int, _vp]),
+    ("hgsfa_crop_extent_batch_device", _int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _int, _int, _vp]),
     ("hgsfa_tile_windows_device", _int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _vp]),
     ("hgsfa_gauss_create", _int, [_vp, _vp, _vp, _vp, _int, _int, _int, C.POINTER(_vp)]),
     ("hgsfa_gauss_destroy", _int, [_vp]),
     ("hgsfa_gauss_regress", _int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("hgsfa_gauss_regress_device", _int, [_vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("hgsfa_cascade_update_device", _int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    ("hgsfa_compact_index_device", _int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    ("hgsfa_gather_rows_device", _int, [_vp, _vp, _vp, _i64, _i64, _vp]),
 ]
 
 _lib = None

@@ -1,0 +1,222 @@
+"""Batched detection cascade on the GPU.
+
+Replaces the per-image / per-scale / per-stage loop of the reference (``FaceDetectUpdated.py:589-761``): for
+every sampling value it builds the window grid, and for each of the first ``num_networks - 5`` stages
+crops the windows, runs the stage's flow (or reuses the previous features when the network is ``None``),
+evaluates the Gaussian regression head, moves / rotates / rescales the boxes, discards windows and compacts
+every per-window array.
+
+Here the windows of ALL scales of ALL images of a batch travel through the stages together, resident on
+the device: grid coordinates are uploaded once, crop -> flow -> head -> controller -> compaction are
+kernels of ``libhgsfa.so``, and the only per-stage host round trip is the 8-byte survivor count.  Windows
+are independent until the per-image purge, so batching changes nothing but the order of evaluation; the
+stable compaction keeps the reference's order (image, scale, window) inside the batch.
+
+What is NOT here yet: the eye-refinement stages (EyeLX / EyeLY need cuicuilco's
+"AgeContrastEnhancement_Avg_Std" patch normalisation) and the age / race / gender stage; detections carry
+the approximate eye positions of ``compute_approximate_eye_boxes_coordinates``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, grid
+from .pipeline import CUT_OFFS_FACE, DEFAULTS
+
+_TYPE_CODE = {"Disc": 0, "PosX": 1, "PosY": 2, "PAng": 3, "Scale": 4}
+
+
+def approximate_eye_coordinates(boxes, angles):
+    """Vectorised ``compute_approximate_eye_boxes_coordinates`` (reference ``face_analysis.py:61-135``),
+    leftscreen_on_left=True; returns (N,4) = left eye x, y, right eye x, y (same float64 operation order)."""
+    x0, y0, x1, y1 = boxes[:, 0], boxes[:, 1], boxes[:, 2], boxes[:, 3]
+    fc_x = (x0 + x1) / 2.0
+    fc_y = (y0 + y1) / 2.0
+    eye_dx = (37.0 / 2.0) * (np.abs(x1 - x0) / 64.0) / (2 * 0.825)
+    eye_dy = (42.0 / 2.0) * (np.abs(y1 - y0) / 64.0) / (2 * 0.825)
+    rad = angles * np.pi / 180
+    er_dx = eye_dx * np.cos(rad) - eye_dy * np.sin(rad)
+    er_dy = eye_dy * np.cos(rad) + eye_dx * np.sin(rad)
+    el_dx = (-1 * eye_dx) * np.cos(rad) - eye_dy * np.sin(rad)
+    el_dy = eye_dy * np.cos(rad) + (-1 * eye_dx) * np.sin(rad)
+    return np.stack([fc_x + el_dx, fc_y - el_dy, fc_x + er_dx, fc_y - er_dy], axis=1)
+
+
+def purge_detections(det, weight_confidences_by_area=True):
+    """``purgue_detected_faces_angles_eyes_confidence`` (reference ``face_analysis.py:186-221``); rows are
+    [x0, y0, x1, y1, angle, eye_l_x, eye_l_y, eye_r_x, eye_r_y, confidence].  Dozens of rows: stays on the host."""
+    det = np.asarray(det, dtype=np.float64).reshape(-1, 10)
+    if len(det) <= 1:
+        return det.copy()
+    conf = det[:, -1]
+    if weight_confidences_by_area:
+        areas = ((det[:, 7] - det[:, 5]) ** 2 + (det[:, 8] - det[:, 6]) ** 2) ** 0.5
+        weighted = (1.0 - conf) * areas
+        weighted = weighted / weighted.max()
+    else:
+        weighted = conf.copy()
+    det = det[np.argsort(weighted)[::-1], :]
+
+    def rel_err(a, b):
+        dl = np.sqrt(((b[0:2] - a[0:2]) ** 2).sum())
+        dr = np.sqrt(((b[2:4] - a[2:4]) ** 2).sum())
+        de = np.sqrt(((b[0:2] - b[2:4]) ** 2).sum())
+        return max(dl, dr) / de
+
+    unique = [det[0]]
+    for row in det:
+        min_d = 10000
+        for row2 in unique:
+            e = rel_err(row[5:9], row2[5:9])
+            if e < min_d:
+                min_d = e
+        if min_d > 0.25:
+            unique.append(row)
+    return np.asarray(unique)
+
+
+class FaceDetector(object):
+    """The face stages of a pipeline (``network_types[:num_networks - 5]``) as one device-resident cascade.
+
+    networks[i] is a ``GpuFlow`` or ``None`` ("None0": reuse the previous features), classifiers[i] a
+    ``GpuGaussianClassifier`` -- exactly what ``pipeline.load_networks_from_pipeline`` returns.
+    """
+
+    def __init__(self, header_net, network_types, networks, classifiers, num_face_stages=None,
+                 cut_offs_face=None, interpolation=_lib.NEAREST, device=0, **overrides):
+        import torch
+        self.torch = torch
+        self.header = tuple(header_net)
+        n_stages = num_face_stages if num_face_stages is not None else len(network_types) - 5
+        self.types = list(network_types[:n_stages])
+        self.networks = list(networks[:n_stages])
+        self.classifiers = list(classifiers[:n_stages])
+        self.cut_offs = list(cut_offs_face if cut_offs_face is not None else CUT_OFFS_FACE)
+        self.cfg = dict(DEFAULTS)
+        self.cfg.update(overrides)
+        self.interpolation = int(interpolation)
+        self.device = int(device)
+        self.dev = torch.device("cuda", self.device)
+        if self.networks and self.networks[0] is None:
+            raise ValueError("the first stage needs a network")
+        self._labels = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _labels_dev(self, clf):
+        t = self._labels.get(id(clf))
+        if t is None:
+            t = self.torch.as_tensor(np.ascontiguousarray(clf.avg_labels, dtype=np.float64), device=self.dev)
+            self._labels[id(clf)] = t
+        return t
+
+    def detect(self, images, smallest_face=0.2, return_trace=False):
+        """images: list of 2-D uint8 arrays (the reference's mode-'L' image, already prescaled).
+        Returns a list (one entry per image) of (M,10) float64 detection arrays after the purge; with
+        ``return_trace`` also a dict with the per-stage window counts and the un-purged detections."""
+        torch = self.torch
+        lib = _lib.load()
+        dev = self.dev
+        net_Dx, net_Dy, net_Dang, net_mins, net_maxs, sw, sh, rw, rh = self.header
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        sp = C.c_void_p(stream) if stream else None
+
+        # ---- window pyramid of every image, one batch ----
+        pyr = [grid.window_pyramid(im.shape[1], im.shape[0], self.header, smallest_face,
+                                   self.cfg["patch_overlap_sampling"], self.cfg["patch_overlap_posx_posy"])
+               for im in images]
+        n0 = int(sum(len(p["coords"]) for p in pyr))
+        counts = np.zeros(len(self.types), dtype=np.int64)
+        if n0 == 0:
+            out = [np.zeros((0, 10)) for _ in images]
+            return (out, dict(stage_counts=counts, raw=[np.zeros((0, 10)) for _ in images])) if return_trace else out
+        coords_h = np.concatenate([p["coords"] for p in pyr])
+        wh_h = np.concatenate([p["patch_wh"] for p in pyr])
+        img_h = np.concatenate([np.full(len(p["coords"]), k, dtype=np.int32) for k, p in enumerate(pyr)])
+
+        imgs_dev = [torch.as_tensor(np.ascontiguousarray(im, dtype=np.uint8), device=dev) for im in images]
+        img_ptrs = torch.tensor([t.data_ptr() for t in imgs_dev], dtype=torch.int64, device=dev)
+        img_hw = torch.tensor([[t.shape[0], t.shape[1]] for t in imgs_dev], dtype=torch.int32, device=dev)
+
+        orig_coords = torch.as_tensor(coords_h, device=dev)
+        orig_angles = torch.zeros(n0, dtype=torch.float64, device=dev)
+        patch_wh = torch.as_tensor(wh_h, device=dev)
+        coords = orig_coords.clone()
+        angles = orig_angles.clone()
+        img_idx = torch.as_tensor(img_h, device=dev)
+        orig_idx = torch.arange(n0, dtype=torch.int32, device=dev)
+        conf = torch.zeros(n0, dtype=torch.float64, device=dev)
+        keep = torch.empty(n0, dtype=torch.uint8, device=dev)
+        src_index = torch.empty(n0, dtype=torch.int32, device=dev)
+        count_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        scratch = torch.empty(max(1, (n0 + 1023) // 1024), dtype=torch.int32, device=dev)
+        sl = None
+        n = n0
+        min_r = net_mins / 0.825
+        max_r = net_maxs / 0.825
+
+        for k, full_type in enumerate(self.types):
+            counts[k] = n
+            if n == 0:
+                continue
+            ntype, serial = full_type[:-1], int(full_type[-1])
+            net, clf = self.networks[k], self.classifiers[k]
+            if net is not None:
+                # patches are re-extracted from the current boxes: after a Disc stage the boxes are unchanged,
+                # so this equals the reference's reuse of the compacted subimages_arr (FaceDetectUpdated.py:674-682)
+                n_pad = (n + _lib.TILE - 1) // _lib.TILE * _lib.TILE
+                patches = torch.empty(n_pad * sw * sh, dtype=torch.uint8, device=dev)
+                _lib.check(lib.hgsfa_crop_extent_batch_device(
+                    C.c_void_p(img_ptrs.data_ptr()), C.c_void_p(img_hw.data_ptr()), C.c_void_p(img_idx.data_ptr()),
+                    C.c_void_p(coords.data_ptr()), C.c_void_p(angles.data_ptr()), n, sw, sh, self.interpolation,
+                    C.c_void_p(patches.data_ptr()), _lib.U8, _lib.TILED, sp))
+                sl = net.execute_torch(patches, layout=_lib.TILED, n=n)
+            elif sl is None:
+                raise ValueError("stage %s reuses features but none were computed" % full_type)
+            D = clf.input_dim
+            if sl.shape[1] < D:
+                raise ValueError("x has dimension %d, should be %d" % (sl.shape[1], D))
+            reg = torch.empty(n, dtype=torch.float64, device=dev)
+            _lib.check(lib.hgsfa_gauss_regress_device(clf.handle, C.c_void_p(sl.data_ptr()), _lib.F32, n, sl.stride(0),
+                                                      C.c_void_p(self._labels_dev(clf).data_ptr()),
+                                                      C.c_void_p(reg.data_ptr()), None, None, None, sp))
+            params = np.array([net_Dx, net_Dy, net_Dang, rw, rh, min_r, max_r, self.cfg["tolerance_posxy_deviation"],
+                               self.cfg["tolerance_scale_deviation"], self.cfg["tolerance_angle_deviation"], 0.825,
+                               self.cut_offs[serial]], dtype=np.float64)
+            _lib.check(lib.hgsfa_cascade_update_device(
+                _TYPE_CODE[ntype], C.c_void_p(coords.data_ptr()), C.c_void_p(angles.data_ptr()),
+                C.c_void_p(reg.data_ptr()), C.c_void_p(orig_coords.data_ptr()), C.c_void_p(orig_angles.data_ptr()),
+                C.c_void_p(orig_idx.data_ptr()), C.c_void_p(patch_wh.data_ptr()), n, _lib.ptr(params),
+                C.c_void_p(keep.data_ptr()), C.c_void_p(conf.data_ptr()) if ntype == "Disc" else None, sp))
+            _lib.check(lib.hgsfa_compact_index_device(C.c_void_p(keep.data_ptr()), n, C.c_void_p(src_index.data_ptr()),
+                                                      C.c_void_p(count_dev.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                                      scratch.numel(), sp))
+            n_new = int(count_dev.item())          # the one host round trip of the stage
+            if n_new < n:
+                def gather(t, row_bytes):
+                    out = torch.empty((n_new,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+                    if n_new:
+                        _lib.check(lib.hgsfa_gather_rows_device(C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                                C.c_void_p(src_index.data_ptr()), n_new, row_bytes, sp))
+                    return out
+                coords = gather(coords, 32)
+                angles = gather(angles, 8)
+                img_idx = gather(img_idx, 4)
+                orig_idx = gather(orig_idx, 4)
+                conf = gather(conf, 8)
+                sl = gather(sl.contiguous(), sl.shape[1] * 4)
+                n = n_new
+
+        # ---- survivors -> detections (host: dozens of rows) ----
+        boxes = coords[:n].cpu().numpy()
+        ang = angles[:n].cpu().numpy()
+        im_of = img_idx[:n].cpu().numpy()
+        cf = conf[:n].cpu().numpy()
+        eyes = approximate_eye_coordinates(boxes, ang) if n else np.zeros((0, 4))
+        raw = np.concatenate([boxes, ang[:, None], eyes, cf[:, None]], axis=1) if n else np.zeros((0, 10))
+        per_image_raw = [raw[im_of == k] for k in range(len(images))]
+        result = [purge_detections(r) if len(r) else np.zeros((0, 10)) for r in per_image_raw]
+        if return_trace:
+            return result, dict(stage_counts=counts, raw=per_image_raw, n_windows=n0)
+        return result

@@ -21,12 +21,25 @@ namespace hgsfa {
 
 constexpr int TILE_W = HGSFA_TILE;
 
+// optional image table: window w reads image img_index[w] (pointer + height / width per image), so that the
+// windows of a whole batch of images are extracted by one launch
+struct ImageTable {
+  const uint8_t* const* ptrs;   // [n_images] device pointers
+  const int* hw;                // [n_images][2] = H, W
+  const int* index;             // [n_windows]
+};
+
 __global__ void crop_index_kernel(const double* __restrict__ boxes, int64_t n, int ow, int oh, int W, int H,
-                                  int* __restrict__ xtab, int* __restrict__ ytab) {
+                                  ImageTable tab_img, int* __restrict__ xtab, int* __restrict__ ytab) {
   const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= 2 * n) return;
   const int64_t w = t >> 1;
   const int axis = int(t & 1);
+  if (tab_img.index) {
+    const int im = tab_img.index[w];
+    H = tab_img.hw[2 * im];
+    W = tab_img.hw[2 * im + 1];
+  }
   const double lo = boxes[w * 4 + axis], hi = boxes[w * 4 + 2 + axis];
   const int cnt = axis ? oh : ow;
   const int size = axis ? H : W;
@@ -94,10 +107,11 @@ __device__ __forceinline__ T cvt_px(uint8_t v) { return T(v); }
 
 // grid (n_tiles, ceil(oh / ROWS)); 256 threads.  OUT_TILED: dst[tile][pixel][128]; else dst[window][pixel].
 template <typename OUT_T, bool OUT_TILED>
-__global__ void __launch_bounds__(256) crop_gather_kernel(const uint8_t* __restrict__ img, int H, int W,
+__global__ void __launch_bounds__(256) crop_gather_kernel(const uint8_t* img, int H, int W,
                                                           const double* __restrict__ boxes,
                                                           const double* __restrict__ angles, int64_t n, int ow, int oh,
-                                                          int filter, const int* __restrict__ xtab,
+                                                          int filter, ImageTable tab_img,
+                                                          const int* __restrict__ xtab,
                                                           const int* __restrict__ ytab, OUT_T* __restrict__ dst,
                                                           int rows_per_cta) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -115,6 +129,12 @@ __global__ void __launch_bounds__(256) crop_gather_kernel(const uint8_t* __restr
     for (int wl = warp; wl < TILE_W; wl += 8) {
       const int64_t w = tile * TILE_W + wl;
       const bool live = w < n;
+      if (live && tab_img.index) {
+        const int im = tab_img.index[w];
+        img = tab_img.ptrs[im];
+        H = tab_img.hw[2 * im];
+        W = tab_img.hw[2 * im + 1];
+      }
       double ang = 0.0;
       if (live && angles) ang = angles[w];
       const bool generic = live && (ang != 0.0 || filter != HGSFA_NEAREST);
@@ -177,10 +197,11 @@ static CropScratch& scratch_for(int device) {
 
 using namespace hgsfa;
 
-extern "C" int hgsfa_crop_extent_device(const uint8_t* d_img, int H, int W, const double* d_boxes,
-                                        const double* d_angles, int64_t n, int ow, int oh, int filter, void* d_out,
-                                        int out_dtype, int out_layout, void* stream) {
-  HG_CHECK(H > 0 && W > 0 && ow > 0 && oh > 0, "hgsfa_crop_extent: bad sizes H=%d W=%d ow=%d oh=%d", H, W, ow, oh);
+namespace {
+
+int crop_launch(const uint8_t* d_img, int H, int W, ImageTable tab, const double* d_boxes, const double* d_angles,
+                int64_t n, int ow, int oh, int filter, void* d_out, int out_dtype, int out_layout, void* stream) {
+  HG_CHECK(ow > 0 && oh > 0, "hgsfa_crop_extent: bad patch size ow=%d oh=%d", ow, oh);
   HG_CHECK(ow <= 1024 && oh <= 1024, "hgsfa_crop_extent: patch size %dx%d too large", ow, oh);
   HG_CHECK(filter == HGSFA_NEAREST || filter == HGSFA_BILINEAR,
            "hgsfa_crop_extent: unsupported interpolation %d (NEAREST=0, BILINEAR=2)", filter);
@@ -188,7 +209,7 @@ extern "C" int hgsfa_crop_extent_device(const uint8_t* d_img, int H, int W, cons
   HG_CHECK(out_layout == HGSFA_ROWMAJOR || (out_layout == HGSFA_TILED && out_dtype != HGSFA_F64),
            "hgsfa_crop_extent: tiled output must be u8 or f32");
   if (n == 0) return 0;
-  HG_CHECK(d_img && d_boxes && d_out, "hgsfa_crop_extent: null buffer");
+  HG_CHECK(d_boxes && d_out, "hgsfa_crop_extent: null buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int device = 0;
   HG_CUDA(cudaGetDevice(&device));
@@ -197,7 +218,7 @@ extern "C" int hgsfa_crop_extent_device(const uint8_t* d_img, int H, int W, cons
   if (sc.ytab.reserve(size_t(n) * oh * sizeof(int))) return 1;
   int* xtab = static_cast<int*>(sc.xtab.p);
   int* ytab = static_cast<int*>(sc.ytab.p);
-  crop_index_kernel<<<(unsigned)ceil_div(2 * n, 128), 128, 0, st>>>(d_boxes, n, ow, oh, W, H, xtab, ytab);
+  crop_index_kernel<<<(unsigned)ceil_div(2 * n, 128), 128, 0, st>>>(d_boxes, n, ow, oh, W, H, tab, xtab, ytab);
   HG_CUDA(cudaGetLastError());
 
   const int rows_per_cta = 8;
@@ -205,7 +226,7 @@ extern "C" int hgsfa_crop_extent_device(const uint8_t* d_img, int H, int W, cons
   const size_t smem = size_t(ow) * (TILE_W + 4);
 #define HG_LAUNCH_CROP(T, TILED)                                                                                   \
   crop_gather_kernel<T, TILED><<<grid, 256, (TILED) ? smem : 0, st>>>(d_img, H, W, d_boxes, d_angles, n, ow, oh, filter, \
-                                                                      xtab, ytab, static_cast<T*>(d_out), rows_per_cta)
+                                                                      tab, xtab, ytab, static_cast<T*>(d_out), rows_per_cta)
   if (out_layout == HGSFA_TILED) {
     if (out_dtype == HGSFA_U8) HG_LAUNCH_CROP(uint8_t, true);
     else HG_LAUNCH_CROP(float, true);
@@ -217,6 +238,26 @@ extern "C" int hgsfa_crop_extent_device(const uint8_t* d_img, int H, int W, cons
 #undef HG_LAUNCH_CROP
   HG_CUDA(cudaGetLastError());
   return 0;
+}
+
+}  // namespace
+
+extern "C" int hgsfa_crop_extent_device(const uint8_t* d_img, int H, int W, const double* d_boxes,
+                                        const double* d_angles, int64_t n, int ow, int oh, int filter, void* d_out,
+                                        int out_dtype, int out_layout, void* stream) {
+  HG_CHECK(H > 0 && W > 0, "hgsfa_crop_extent: bad image size H=%d W=%d", H, W);
+  HG_CHECK(d_img || n == 0, "hgsfa_crop_extent: null image");
+  return crop_launch(d_img, H, W, ImageTable{nullptr, nullptr, nullptr}, d_boxes, d_angles, n, ow, oh, filter, d_out,
+                     out_dtype, out_layout, stream);
+}
+
+extern "C" int hgsfa_crop_extent_batch_device(const uint8_t* const* d_img_ptrs, const int32_t* d_img_hw,
+                                              const int32_t* d_img_index, const double* d_boxes, const double* d_angles,
+                                              int64_t n, int ow, int oh, int filter, void* d_out, int out_dtype,
+                                              int out_layout, void* stream) {
+  HG_CHECK((d_img_ptrs && d_img_hw && d_img_index) || n == 0, "hgsfa_crop_extent_batch: null image table");
+  return crop_launch(nullptr, 1, 1, ImageTable{d_img_ptrs, d_img_hw, d_img_index}, d_boxes, d_angles, n, ow, oh, filter,
+                     d_out, out_dtype, out_layout, stream);
 }
 
 extern "C" int hgsfa_crop_extent(const uint8_t* img, int H, int W, const double* boxes, const double* angles,

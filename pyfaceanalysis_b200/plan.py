@@ -677,9 +677,9 @@ def compile_flow(flow, input_dim=None, igsfa_mode="auto"):
         """children: list of child nodes, consuming consecutive slices of the current logical vector."""
         nonlocal pending_layers
         dims = [node_input_dim(ch) for ch in children]
-        if sum(dims) != len(cols):
-            raise ValueError("%s: x has dimension %d, should be %d" % ("Layer", len(cols), sum(dims)))
         seqs = [_child_sequence(ch) for ch in children]
+        if not pending_layers and sum(dims) != len(cols):
+            raise ValueError("%s: x has dimension %d, should be %d" % ("Layer", len(cols), sum(dims)))
         if pending_layers:
             # a Layer directly after an expansion-only Layer with the same partition: fuse per field
             fields, gathers = pending_layers

@@ -90,7 +90,20 @@ def spec_tiny(input_xy=(16, 16), clone_first=True):
     return dict(name="tiny_%dx%d" % input_xy, input_xy=input_xy, layers=L)
 
 
-SPECS = {"U11L_64": spec_u11l_64, "U11L_96": spec_u11l_96, "tiny": spec_tiny}
+def spec_s5l_64():
+    """Small 5-layer 64x64 network (same vocabulary as U11L_64) for cascade tests on the CPU oracle."""
+    f_low = ["identity", "unsigned_08expo"]
+    f_high = ["identity", "unsigned_08expo", "s8QT"]
+    L = []
+    L.append(_layer((64, 64), (8, 8), (8, 8), 12, 4, f_low))        # -> 8x8
+    L.append(_layer((8, 8), (2, 2), (2, 2), 16, 5, f_low))          # -> 4x4
+    L.append(_layer((4, 4), (2, 2), (2, 2), 20, 6, f_high))         # -> 2x2
+    L.append(_layer((2, 2), (2, 2), (2, 2), 24, 8, f_high))         # -> 1x1
+    L.append(_layer((1, 1), (1, 1), (1, 1), 24, 8, f_high))
+    return dict(name="S5L_64", input_xy=(64, 64), layers=L)
+
+
+SPECS = {"U11L_64": spec_u11l_64, "U11L_96": spec_u11l_96, "tiny": spec_tiny, "S5L_64": spec_s5l_64}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -224,8 +237,9 @@ def _fit_igsfa(x, funcs, out_dim, J, rng):
     return node, np.concatenate([s_n, r], axis=1)
 
 
-def make_flow(spec, seed=0, n_train=None, vary_J=True, clip_sigmas=4.0, verbose=False):
-    """Build and fit a synthetic flow.  Returns an ``mdp.Flow``-shaped object (``.flow`` node list)."""
+def make_flow(spec, seed=0, n_train=None, vary_J=True, clip_sigmas=4.0, verbose=False, train_patches=None):
+    """Build and fit a synthetic flow.  Returns an ``mdp.Flow``-shaped object (``.flow`` node list).
+    ``train_patches`` (n, w*h) replaces the default band-limited-noise training set."""
     if isinstance(spec, str):
         spec = SPECS[spec]()
     rng = np.random.default_rng(seed)
@@ -238,7 +252,11 @@ def make_flow(spec, seed=0, n_train=None, vary_J=True, clip_sigmas=4.0, verbose=
         ch = L["out_dim"]
     if n_train is None:
         n_train = max(1000, 12 * dmax)
-    X = synthetic_patches(n_train, (w, h), seed + 1).astype(np.float64)
+    if train_patches is not None:
+        X = np.asarray(train_patches, dtype=np.float64)
+        n_train = X.shape[0]
+    else:
+        X = synthetic_patches(n_train, (w, h), seed + 1).astype(np.float64)
     nodes = []
     ch = 1
     for li, L in enumerate(spec["layers"]):

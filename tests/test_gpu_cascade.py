@@ -1,0 +1,159 @@
+"""GPU parity of the cascade controller kernels (csrc/cascade.cu) and of the whole batched cascade against
+the oracle's statement-by-statement restatement of the reference loop."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cascade_models as cm
+from oracle import cascade as ocascade
+from oracle import controller as octl
+
+pytestmark = pytest.mark.gpu
+CUT = [0.99, 0.95, 0.85, 0.8, 0.7, 0.6, 0.5, 0.45, 0.10, 0.6]   # like --last_cut_off_face (FaceDetectUpdated.py:434-438)
+
+
+def _t(a):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+
+
+@pytest.mark.parametrize("ntype", ["Disc", "PosX", "PosY", "PAng", "Scale"])
+def test_controller_kernel_bit_exact(ntype):
+    from pyfaceanalysis_b200 import _lib
+    from pyfaceanalysis_b200.cascade import _TYPE_CODE
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    n_orig, n = 500, 333
+    pw = rng.uniform(20, 400, n_orig)
+    orig = np.stack([rng.uniform(0, 900, n_orig), rng.uniform(0, 700, n_orig)], axis=1)
+    orig = np.concatenate([orig, orig + pw[:, None] - 1], axis=1)
+    oidx = np.sort(rng.choice(n_orig, n, replace=False)).astype(np.int32)
+    coords = orig[oidx] + rng.normal(0, 3, (n, 4))
+    angles = rng.normal(0, 10, n)
+    reg = {"Disc": rng.uniform(0, 1, n), "PosX": rng.normal(0, 25, n), "PosY": rng.normal(0, 12, n),
+           "PAng": rng.normal(0, 15, n), "Scale": rng.uniform(0.6, 1.1, n)}[ntype]
+    if ntype == "Disc":
+        reg[::17] = np.nan
+    hdr = cm.HEADER
+    params = np.array([hdr[0], hdr[1], hdr[2], hdr[7], hdr[8], hdr[3] / 0.825, hdr[4] / 0.825, 1.1, 1.1, 1.1, 0.825, 0.45])
+    # oracle (per-scale scalars -> evaluate window by window, as the windows of several scales are mixed)
+    ref_c, ref_a, ref_wrong = coords.copy(), angles.copy(), np.zeros(n, dtype=bool)
+    for i in range(n):
+        c1, a1 = octl.update_coordinates(ntype, ref_c[i:i + 1], ref_a[i:i + 1], reg[i:i + 1], hdr[7], hdr[8], 0.825)
+        ref_a[i] = a1[0]
+        p = pw[oidx[i]]
+        ref_wrong[i] = octl.patches_to_discard(ntype, ref_c[i:i + 1], ref_a[i:i + 1], reg[i:i + 1], np.sqrt(p ** 2 + p ** 2),
+                                               oidx[i:i + 1], orig, np.zeros(n_orig), hdr[0] * p / hdr[7], hdr[1] * p / hdr[8],
+                                               1.1, hdr[4] / 0.825, hdr[3] / 0.825, 1.1, hdr[2], 1.1, 0.45)[0]
+    d_c, d_a, d_r = _t(coords), _t(angles), _t(reg)
+    d_o, d_oa, d_oi = _t(orig), _t(np.zeros(n_orig)), _t(oidx)
+    d_wh = _t(np.stack([pw, pw], axis=1))
+    import torch
+    keep = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+    conf = torch.zeros(n, dtype=torch.float64, device="cuda:0")
+    _lib.check(lib.hgsfa_cascade_update_device(_TYPE_CODE[ntype], C.c_void_p(d_c.data_ptr()), C.c_void_p(d_a.data_ptr()),
+                                               C.c_void_p(d_r.data_ptr()), C.c_void_p(d_o.data_ptr()), C.c_void_p(d_oa.data_ptr()),
+                                               C.c_void_p(d_oi.data_ptr()), C.c_void_p(d_wh.data_ptr()), n, _lib.ptr(params),
+                                               C.c_void_p(keep.data_ptr()), C.c_void_p(conf.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_c.cpu().numpy(), ref_c)            # bit-exact float64
+    assert np.array_equal(d_a.cpu().numpy(), ref_a)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), ~ref_wrong)
+    assert 0 < ref_wrong.sum() < n
+    if ntype == "Disc":
+        assert np.array_equal(conf.cpu().numpy(), reg, equal_nan=True)
+        assert (~ref_wrong)[::17].all()                          # NaN >= cut_off is False: kept
+
+
+@pytest.mark.parametrize("n", [1, 1023, 1024, 1025, 70001])
+def test_compaction_is_stable_boolean_indexing(n):
+    import torch
+    from pyfaceanalysis_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    keep = (rng.random(n) < 0.37).astype(np.uint8)
+    rows = rng.standard_normal((n, 6)).astype(np.float32)
+    d_keep, d_rows = _t(keep), _t(rows)
+    idx = torch.empty(n, dtype=torch.int32, device="cuda:0")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+    scratch = torch.empty((n + 1023) // 1024, dtype=torch.int32, device="cuda:0")
+    _lib.check(lib.hgsfa_compact_index_device(C.c_void_p(d_keep.data_ptr()), n, C.c_void_p(idx.data_ptr()),
+                                              C.c_void_p(cnt.data_ptr()), C.c_void_p(scratch.data_ptr()), scratch.numel(), None))
+    m = int(cnt.item())
+    assert m == int(keep.sum())
+    assert np.array_equal(idx[:m].cpu().numpy(), np.nonzero(keep)[0])
+    out = torch.empty((m, 6), dtype=torch.float32, device="cuda:0")
+    _lib.check(lib.hgsfa_gather_rows_device(C.c_void_p(d_rows.data_ptr()), C.c_void_p(out.data_ptr()),
+                                            C.c_void_p(idx.data_ptr()), m, 24, None))
+    assert np.array_equal(out.cpu().numpy(), rows[keep == 1])
+
+
+def _gpu_models(m):
+    from pyfaceanalysis_b200 import GpuFlow, GpuGaussianClassifier
+    flows, heads = {}, {}
+    nets = [None if f is None else flows.setdefault(id(f), GpuFlow(f)) for f in m["networks"]]
+    clfs = [None if c is None else heads.setdefault(id(c), GpuGaussianClassifier(c)) for c in m["classifiers"]]
+    return nets, clfs
+
+
+def test_batched_cascade_matches_reference_loop():
+    """Config-1-style end to end: window pyramid -> 17 stages -> detections, 3 images in one batch.
+
+    (1) The reference loop (oracle, per image / per scale) driven with the GPU flow and head must give
+        EXACTLY what the batched device-resident cascade gives: same crops, same controller arithmetic,
+        same order -- batching and compaction change nothing.
+    (2) Against the pure float64 oracle the survivor counts per stage are equal and the detections agree;
+        float32 features perturb regressed angles / positions at the 1e-5 level, which after a later
+        NEAREST re-crop can flip single pixels of a patch, so a minority of rows may differ slightly more.
+    """
+    from pyfaceanalysis_b200.cascade import FaceDetector
+    m = cm.cached_models()
+    nets, clfs = _gpu_models(m)
+    gpu_flow = {id(f): g for f, g in zip(m["networks"], nets) if f is not None}
+    gpu_head = {id(c): g for c, g in zip(m["classifiers"], clfs) if c is not None}
+    det = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=CUT)
+    images = [cm.test_scene(seed)[0] for seed in (5, 6, 7)]
+    got, trace = det.detect(images, smallest_face=0.2, return_trace=True)
+    ref_counts = np.zeros(m["num_face_stages"], dtype=np.int64)
+    hyb_counts = np.zeros(m["num_face_stages"], dtype=np.int64)
+    close_rows = total_rows = 0
+    for k, img in enumerate(images):
+        hyb, trh = ocascade.detect_image(
+            img, m["header"], m["network_types"], m["networks"], m["classifiers"], 0.2, m["num_face_stages"],
+            cut_offs_face=CUT,
+            flow_execute=lambda f, x: gpu_flow[id(f)].execute(x.astype(np.uint8), out_dtype=np.float32).astype(np.float64),
+            regression=lambda c, x, lab: gpu_head[id(c)].regression(x.astype(np.float32), lab))
+        hyb_counts += trh["stage_counts"]
+        assert trace["raw"][k].shape == trh["raw"].shape
+        assert np.allclose(trace["raw"][k], trh["raw"], rtol=0, atol=1e-9), np.abs(trace["raw"][k] - trh["raw"]).max()
+        assert np.allclose(got[k], hyb, rtol=0, atol=1e-9)
+
+        purged, tr = ocascade.detect_image(img, m["header"], m["network_types"], m["networks"], m["classifiers"], 0.2,
+                                           m["num_face_stages"], cut_offs_face=CUT)
+        ref_counts += tr["stage_counts"]
+        raw = trace["raw"][k]
+        assert raw.shape == tr["raw"].shape, (k, raw.shape, tr["raw"].shape)
+        d = np.abs(raw - tr["raw"])
+        assert d[:, :9].max() < 1.0 and d[:, 9].max() < 0.15            # boxes within a pixel, confidence close
+        close_rows += int((d.max(axis=1) < 2e-3).sum())
+        total_rows += len(raw)
+        assert got[k].shape == purged.shape
+    assert np.array_equal(trace["stage_counts"], hyb_counts)
+    # survivors per stage are the natural parity metric of the cascade
+    assert np.array_equal(trace["stage_counts"], ref_counts), (trace["stage_counts"], ref_counts)
+    assert close_rows >= 0.7 * total_rows, (close_rows, total_rows)
+    assert trace["n_windows"] == 3 * 292 and ref_counts[-1] > 0
+
+
+def test_empty_and_tiny_inputs():
+    from pyfaceanalysis_b200.cascade import FaceDetector
+    m = cm.cached_models()
+    nets, clfs = _gpu_models(m)
+    det = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=[2.0] * 10)   # nothing discarded by Disc
+    img = cm.test_scene(9, 120, 160, 1)[0]
+    got, trace = det.detect([img], smallest_face=0.5, return_trace=True)
+    assert trace["stage_counts"][0] == trace["n_windows"] > 0
+    det2 = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=[-1.0] * 10)  # everything discarded at stage 0
+    got2, trace2 = det2.detect([img], smallest_face=0.5, return_trace=True)
+    assert got2[0].shape == (0, 10) and trace2["stage_counts"][1:].sum() == 0
