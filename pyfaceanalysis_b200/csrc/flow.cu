@@ -14,6 +14,7 @@
 // their activations stay L2-resident between launches; the last layers, which have only a few nodes,
 // run once per back_chunk windows so that every launch still fills the 148 SMs.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -45,6 +46,55 @@ __global__ void __launch_bounds__(256) tile_windows_kernel(const SRC* __restrict
   for (int idx = tid; idx < TILE * 64; idx += 256) {
     const int f = idx >> 7, w = idx & 127;
     if (f0 + f < dim) dst[(tile * dim + f0 + f) * TILE + w] = s[f][w];
+  }
+}
+
+// uint8 fast path (what the detector and the benchmark feed): 128 windows x 128 features per CTA.
+// Row-major rows are read as 16-byte vectors, the 128 x 128 byte block is transposed in 4 x 4 byte blocks
+// with PRMT, and every tiled feature row is written as coalesced 32-bit words.  The staging tile is
+// XOR-swizzled so that the column reads of the transpose are bank-conflict free.
+__global__ void __launch_bounds__(256) tile_windows_u8_kernel(const uint8_t* __restrict__ src, int64_t n, int64_t dim,
+                                                              int64_t ld, uint8_t* __restrict__ dst) {
+  __shared__ uint32_t s[TILE][33];
+  const int64_t tile = blockIdx.y;
+  const int f0 = blockIdx.x * 128;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // phase 1: 128 rows x 8 chunks of 16 bytes
+  for (int idx = tid; idx < TILE * 8; idx += 256) {
+    const int w = idx >> 3, c = idx & 7;
+    const int64_t gw = tile * TILE + w;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (gw < n) {
+      const uint8_t* p = src + gw * ld + f0 + c * 16;
+      if (f0 + c * 16 + 16 <= dim) {
+        v = __ldg(reinterpret_cast<const uint4*>(p));
+      } else {
+        uint32_t tmp[4] = {0u, 0u, 0u, 0u};
+        for (int b = 0; b < 16; ++b)
+          if (f0 + c * 16 + b < dim) tmp[b >> 2] |= uint32_t(p[b]) << (8 * (b & 3));
+        v = make_uint4(tmp[0], tmp[1], tmp[2], tmp[3]);
+      }
+    }
+    const int sw = w >> 5;
+    s[w][(c * 4 + 0) ^ sw] = v.x; s[w][(c * 4 + 1) ^ sw] = v.y; s[w][(c * 4 + 2) ^ sw] = v.z; s[w][(c * 4 + 3) ^ sw] = v.w;
+  }
+  __syncthreads();
+  // phase 2: lane = group of 4 windows, warp strides over groups of 4 features
+  const int q = lane;
+  for (int p = warp; p < 32; p += 8) {
+    const int col = p ^ (q >> 3);
+    const uint32_t r0 = s[4 * q + 0][col], r1 = s[4 * q + 1][col], r2 = s[4 * q + 2][col], r3 = s[4 * q + 3][col];
+    // 4 x 4 byte transpose: t_j = byte j of (r0, r1, r2, r3)
+    const uint32_t a0 = __byte_perm(r0, r1, 0x5140), a1 = __byte_perm(r0, r1, 0x7362);   // (r0.b0 r1.b0 r0.b1 r1.b1), (b2 b2 b3 b3)
+    const uint32_t b0 = __byte_perm(r2, r3, 0x5140), b1 = __byte_perm(r2, r3, 0x7362);
+    const uint32_t t0 = __byte_perm(a0, b0, 0x5410), t1 = __byte_perm(a0, b0, 0x7632);
+    const uint32_t t2 = __byte_perm(a1, b1, 0x5410), t3 = __byte_perm(a1, b1, 0x7632);
+    const int f = f0 + 4 * p;
+    uint32_t* o = reinterpret_cast<uint32_t*>(dst + (tile * dim + f) * TILE) + q;
+    if (f + 0 < dim) o[0 * (TILE / 4)] = t0;
+    if (f + 1 < dim) o[1 * (TILE / 4)] = t1;
+    if (f + 2 < dim) o[2 * (TILE / 4)] = t2;
+    if (f + 3 < dim) o[3 * (TILE / 4)] = t3;
   }
 }
 
@@ -124,6 +174,8 @@ struct hgsfa_plan_s {
   int split = 0;                     // ops [0, split) run per front chunk, [split, n) per back chunk
   int64_t launches = 0;
   double last_ms = 0.0;
+  int sm_count = 148;
+  int max_npc = 16;
 };
 
 namespace {
@@ -147,13 +199,25 @@ int launch_layer(hgsfa_plan_s* pl, OpHost& op, const void* xin, float* xout, int
   if (ntiles <= 0) return 0;
   const int v = sizeof(IN_T) == 1 ? 1 : 0;
   OpDev d = op.dev;
+  // nodes per CTA, chosen per launch: as many as possible (the first load of a CTA is exposed, later ones
+  // are prefetched behind the previous node's FMAs) while the grid still covers the SMs several times over
+  {
+    const int64_t groups = ceil_div(ntiles, d.twc);
+    int64_t npc = (groups * d.n_nodes) / (int64_t(pl->sm_count) * 4);
+    if (npc < 1) npc = 1;
+    if (npc > pl->max_npc) npc = pl->max_npc;
+    if (npc > d.n_nodes) npc = d.n_nodes;
+    d.npc = (int)npc;
+  }
   int ns = 1;
-  layout_op(d, op.scratch_floats, (int)sizeof(IN_T), &ns);
+  const size_t smem = layout_op(d, op.scratch_floats, (int)sizeof(IN_T), &ns);
+  HG_CHECK(smem > 0 && smem <= op.smem_bytes[v], "layer launch needs %zu bytes of shared memory, reserved %zu", smem,
+           op.smem_bytes[v]);
   dim3 grid((unsigned)ceil_div(ntiles, d.twc), (unsigned)ceil_div(d.n_nodes, d.npc));
   if (op.wide)
-    layer_kernel<IN_T, 32><<<grid, THREADS, op.smem_bytes[v], st>>>(d, static_cast<const IN_T*>(xin), xout, ntiles);
+    layer_kernel<IN_T, 32><<<grid, 32 * d.warps, smem, st>>>(d, static_cast<const IN_T*>(xin), xout, ntiles);
   else
-    layer_kernel<IN_T, 16><<<grid, THREADS, op.smem_bytes[v], st>>>(d, static_cast<const IN_T*>(xin), xout, ntiles);
+    layer_kernel<IN_T, 16><<<grid, 32 * d.warps, smem, st>>>(d, static_cast<const IN_T*>(xin), xout, ntiles);
   pl->launches++;
   HG_CUDA(cudaGetLastError());
   return 0;
@@ -206,7 +270,8 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
     OpHost op{};
     OpDev& d = op.dev;
     d.n_nodes = (int)oh[0]; d.d_in = (int)oh[1]; d.in_dim = (int)oh[2]; d.out_dim = (int)oh[3];
-    d.n_passes = (int)oh[4]; d.shared = (int)oh[5]; d.n_rows = (int)oh[6]; d.twc = (int)oh[7];
+    d.n_passes = (int)oh[4]; d.shared = (int)(oh[5] & 0xff); d.warps = (int)((oh[5] >> 8) & 0xff); d.n_rows = (int)oh[6];
+    d.twc = (int)oh[7];
     op.alg_flops = oh[8]; op.exe_flops = oh[9];
     d.npc = (int)oh[10]; d.n_runs = (int)oh[11];
     {
@@ -218,7 +283,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
     const bool sane = d.n_nodes > 0 && d.n_nodes <= 65535 * 64 && d.d_in > 0 && d.d_in < 32768 && d.in_dim == cur_dim &&
                       d.out_dim > 0 && d.n_passes >= 1 && d.n_passes <= MAX_PASSES &&
                       (d.twc == 1 || d.twc == 2 || d.twc == 4 || d.twc == 8 || d.twc == 16) && d.n_rows >= 0 && d.npc >= 1 &&
-                      d.n_runs >= 1 && d.n_runs <= d.d_in && d.param_floats > 0 && d.param_floats % 4 == 0 &&
+                      (d.warps == 4 || d.warps == 8) && d.n_runs >= 1 && d.n_runs <= d.d_in && d.param_floats > 0 && d.param_floats % 4 == 0 &&
                       d.n_terms > 0;
     if (!sane)
       return plan_fail(pl, "op %lld has an inconsistent header (nodes=%d d_in=%d in_dim=%d expected %lld twc=%d)",
@@ -258,7 +323,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       dp.term_off = (int)ph[10]; dp.n_seg = (int)ph[11]; dp.SW = (int)ph[14];
       const bool psane =
           dp.K > 0 && (dp.NT == 8 || dp.NT == 16 || dp.NT == 24 || dp.NT == 32) && dp.NTL >= 1 && dp.KS >= 1 &&
-          dp.TW >= 1 && dp.NTL * dp.KS * dp.TW == WARPS && dp.Npad == dp.NT * dp.NTL && (dp.SW == 1 || dp.SW == 2) &&
+          dp.TW >= 1 && dp.NTL * dp.KS * dp.TW == d.warps && dp.Npad == dp.NT * dp.NTL && (dp.SW == 1 || dp.SW == 2) &&
           (dp.SW == 1 || dp.NT <= 16) && d.twc % dp.SW == 0 &&
           (dp.KS & (dp.KS - 1)) == 0 && (dp.dst & (DST_GLOBAL | DST_ROWS)) && dp.row0 >= 0 &&
           (!(dp.dst & DST_ROWS) || dp.row0 + dp.Npad <= d.n_rows) && dp.w_off >= 0 && dp.w_off % 4 == 0 && dp.b_off >= 0 &&
@@ -292,11 +357,12 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       dp.n_valid = reinterpret_cast<const int*>(dev_ptr(n_valid));
       dp.col_off = reinterpret_cast<const int*>(dev_ptr(col_off));
       if (dp.NT * dp.SW > 16) op.wide = true;
-      if (dp.KS > 1) op.scratch_floats = std::max(op.scratch_floats, (WARPS / 2) * dp.SW * dp.NT * TILE);
+      if (dp.KS > 1) op.scratch_floats = std::max(op.scratch_floats, (d.warps / 2) * dp.SW * dp.NT * TILE);
     }
     if (!cur.ok) break;
     for (int v = 0; v < 2; ++v) {
       OpDev tmp = d;
+      tmp.npc = 2;   // worst case for the reservation: two stages whenever they fit
       op.smem_bytes[v] = layout_op(tmp, op.scratch_floats, v ? 1 : 4, &op.nstages[v]);
     }
     if (op.smem_bytes[0] == 0)
@@ -317,6 +383,11 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
   for (cudaError_t e : es)
     if (e != cudaSuccess)
       return plan_fail(pl, "cannot reserve %zu bytes of dynamic shared memory: %s", max_smem, cudaGetErrorString(e));
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) pl->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("HGSFA_MAX_NPC")) pl->max_npc = std::max(1, atoi(e));
+  }
   // back segment = trailing ops with few nodes: they need many windows per launch to fill 148 SMs
   pl->split = (int)pl->ops.size();
   while (pl->split > 0 && pl->ops[pl->split - 1].dev.n_nodes <= 8) pl->split--;
@@ -401,7 +472,10 @@ extern "C" int hgsfa_tile_windows_device(const void* d_src, int dtype, int64_t n
   if (n == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((unsigned)ceil_div(dim, 64), (unsigned)ceil_div(n, TILE));
-  if (dtype == HGSFA_U8 && dst_dtype == HGSFA_U8)
+  if (dtype == HGSFA_U8 && dst_dtype == HGSFA_U8 && ld % 16 == 0 && (reinterpret_cast<uintptr_t>(d_src) & 15) == 0) {
+    dim3 g8((unsigned)ceil_div(dim, 128), (unsigned)ceil_div(n, TILE));
+    tile_windows_u8_kernel<<<g8, 256, 0, st>>>((const uint8_t*)d_src, n, dim, ld, (uint8_t*)d_dst);
+  } else if (dtype == HGSFA_U8 && dst_dtype == HGSFA_U8)
     tile_windows_kernel<uint8_t, uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)d_src, n, dim, ld, (uint8_t*)d_dst);
   else if (dtype == HGSFA_U8 && dst_dtype == HGSFA_F32)
     tile_windows_kernel<uint8_t, float><<<grid, 256, 0, st>>>((const uint8_t*)d_src, n, dim, ld, (float*)d_dst);

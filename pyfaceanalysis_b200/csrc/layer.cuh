@@ -29,7 +29,7 @@ namespace hgsfa {
 
 constexpr int TILE = HGSFA_TILE;   // windows per tile
 constexpr int MAX_PASSES = 4;
-constexpr int WARPS = 8;
+constexpr int WARPS = 8;          // most warps a CTA is launched with; an op runs with op.warps of them (4 or 8)
 constexpr int THREADS = WARPS * 32;
 
 enum TermOp { OP_ID = 0, OP_MUL = 1, OP_ABSPOW = 2, OP_SGNPOW = 3, OP_MUL3 = 4, OP_ABS = 5, OP_CLIP = 6,
@@ -56,7 +56,7 @@ struct PassDev {
 
 struct OpDev {
   int n_nodes, d_in, in_dim, out_dim, n_passes, shared, n_rows, twc;
-  int npc, n_runs, nstages, param_floats, n_terms;
+  int npc, n_runs, nstages, param_floats, n_terms, warps;
   float clip_lo, clip_hi;
   const Run* runs;        // [n_nodes][n_runs]
   const int* out_col;     // [n_nodes]
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(THREADS, (NTMAX <= 16 ? 2 : 1))
   {  // term table of all passes (shared by every node of the op)
     const uint2* src = reinterpret_cast<const uint2*>(op.terms);
     uint2* dst = reinterpret_cast<uint2*>(smem + op.sm_terms);
-    for (int i = tid; i < op.n_terms; i += THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < op.n_terms; i += blockDim.x) dst[i] = __ldg(src + i);
   }
   __syncthreads();
 

@@ -29,7 +29,7 @@ from . import expansions as ex
 
 TILE = 128
 MAX_PASSES = 4
-WARPS = 8        # warps per CTA of layer_kernel (csrc/layer.cuh)
+WARPS = 8        # most warps per CTA of layer_kernel (csrc/layer.cuh); an op runs with op.warps = 4 or 8
 DST_GLOBAL, DST_ROWS = 1, 2
 SMEM_TARGET = 113 * 1024    # per-CTA shared memory that still lets two CTAs share an SM
 SMEM_LIMIT = 227 * 1024
@@ -297,7 +297,7 @@ class _Lowerer(object):
         mode = self.igsfa_mode
         if mode == "auto":
             # the single folded pass has no shared-row round trip, no second epilogue and no K-split
-            # reduction; measured on B200 it wins until it executes ~1.5x the flops of the two-pass form
+            # reduction; measured on B200 it wins until it executes ~1.7x the flops of the two-pass form
             mode = "fold" if cost_fold <= FOLD_BIAS * cost_two else "two_pass"
         if mode == "fold":
             Tf = np.concatenate([T, _identity_terms(missing)]) if missing else T
@@ -373,6 +373,7 @@ class OpSpec(object):
         self.n_rows = 0
         self.twc = 1
         self.npc = 1
+        self.warps = 8
         self.n_runs = 1
         self.runs = None
         self.param_floats = 0
@@ -388,7 +389,7 @@ def _choose_tile(n_real):
     Minimises padded columns; on ties prefers NT <= 16 (register footprint that keeps two CTAs per SM),
     then the larger NT (fewer shared-memory reads per FMA)."""
     best = None
-    for ntl in (1, 2, 4, 8):
+    for ntl in (1, 2, 4):
         for nt in (8, 16, 24, 32):
             if nt * ntl < n_real:
                 continue
@@ -505,28 +506,30 @@ def _gather_runs(gather_row):
     return runs
 
 
-def _op_smem(op, twc, el=4, stages=1):
+def _op_smem(op, twc, el=4, stages=1, warps=None):
     """Shared memory of layer_kernel for this op (mirrors layout_op in csrc/flow.cu)."""
+    warps = warps or op.warps
+
     def up(x):
         return (x + 127) // 128 * 128
     n_terms = sum(ps["K"] for ps in op.passes)
     scratch = 0
     for ps in op.passes:
-        sw, tw, ks = _pass_split(ps, twc)
+        sw, tw, ks = _pass_split(ps, twc, warps)
         if ks > 1:
-            scratch = max(scratch, (WARPS // 2) * sw * ps["NT"] * TILE * 4)
+            scratch = max(scratch, (warps // 2) * sw * ps["NT"] * TILE * 4)
     raw = op.d_in * TILE * el
     stage = up(twc * raw + op.param_floats * 4)
     return 128 + up(n_terms * 8) + up(twc * op.n_rows * TILE * 4) + up(scratch) + stages * stage
 
 
-def _pass_split(ps, twc):
+def _pass_split(ps, twc, warps):
     """(SW, TW, KS): tile slots per warp, slot groups processed concurrently, K-split, with
-    TW * NTL * KS == WARPS.  Two slots per warp (a 8 windows x NT register tile) halve the weight reads per
+    TW * NTL * KS == warps.  Two slots per warp (a 8 windows x NT register tile) halve the weight reads per
     FMA; they are used whenever the accumulators still fit (NT <= 16)."""
     sw = 2 if (ps["NT"] <= 16 and twc >= 2 and TWO_SLOTS) else 1
-    tw = max(1, min(twc // sw, WARPS // ps["NTL"]))
-    return sw, tw, WARPS // (ps["NTL"] * tw)
+    tw = max(1, min(twc // sw, warps // ps["NTL"]))
+    return sw, tw, warps // (ps["NTL"] * tw)
 
 
 import os as _os
@@ -534,10 +537,15 @@ import os as _os
 # tuning switches (environment overrides are for experiments; defaults are what the measurements favour)
 TWO_SLOTS = _os.environ.get("HGSFA_TWO_SLOTS", "1") != "0"
 FOLD_MEANS = _os.environ.get("HGSFA_FOLD_MEANS", "1") != "0"
+SMALL_CTAS = _os.environ.get("HGSFA_SMALL_CTAS", "1") != "0"
 
 
 def _decompose(op):
-    """Choose tile slots per CTA, nodes per CTA and the per-pass warp decomposition."""
+    """Choose warps per CTA, tile slots per CTA and the per-pass warp decomposition.
+
+    Measured on B200 (profiles/README_r01.md): two 4-warp CTAs per SM beat one 8-warp CTA -- the per-node
+    barrier, the mbarrier wait and the epilogue of one CTA overlap the FMA loops of the other -- so an op
+    uses 4-warp CTAs whenever two of them fit in shared memory, and an 8-warp CTA otherwise."""
     d_pad = -(-op.d_in // 4) * 4
     off = d_pad
     for ps in op.passes:
@@ -546,21 +554,36 @@ def _decompose(op):
         ps["w_off"] = off
         off += ps["K"] * ps["Npad"]
     op.param_floats = -(-off // 4) * 4
-    # enough slots that no pass needs a K-split, then as many as shared memory allows
-    want = 1
-    for ps in op.passes:
-        sw = 2 if (ps["NT"] <= 16 and TWO_SLOTS) else 1
-        want = max(want, min(16, sw * (WARPS // ps["NTL"])))
     wide = any(ps["NT"] > 16 or (ps["NT"] == 16 and TWO_SLOTS) for ps in op.passes)
-    budget = SMEM_LIMIT if wide else SMEM_TARGET
-    cands = [t for t in (16, 8, 4, 2, 1) if t <= want]
-    fits = [t for t in cands if _op_smem(op, t) <= budget] or [t for t in cands if _op_smem(op, t) <= SMEM_LIMIT]
-    if not fits:
-        raise UnsupportedFlow("a receptive field of %d inputs does not fit in shared memory" % op.d_in)
-    op.twc = fits[0]
+
+    def best_twc(warps, budget):
+        # enough slots that no pass needs a K-split, then as many as shared memory allows
+        want = 1
+        for ps in op.passes:
+            sw = 2 if (ps["NT"] <= 16 and TWO_SLOTS) else 1
+            want = max(want, min(16, sw * max(1, warps // ps["NTL"])))
+        cands = [t for t in (16, 8, 4, 2, 1) if t <= want]
+        fits = [t for t in cands if _op_smem(op, t, warps=warps) <= budget]
+        return fits[0] if fits else None
+
+    choice = None
+    if SMALL_CTAS and all(ps["NTL"] <= 4 for ps in op.passes):
+        # registers: a wide kernel (255 regs) allows 2 x 128 threads per SM, a narrow one 4 x 128
+        per_sm = 2 if wide else 4
+        t = best_twc(4, SMEM_LIMIT // per_sm - 1024)
+        if t is None and not wide:
+            t = best_twc(4, SMEM_LIMIT // 2 - 1024)
+        if t is not None:
+            choice = (4, t)
+    if choice is None:
+        t = best_twc(8, SMEM_LIMIT if wide else SMEM_TARGET) or best_twc(8, SMEM_LIMIT)
+        if t is None:
+            raise UnsupportedFlow("a receptive field of %d inputs does not fit in shared memory" % op.d_in)
+        choice = (8, t)
+    op.warps, op.twc = choice
     for ps in op.passes:
-        ps["SW"], ps["TW"], ps["KS"] = _pass_split(ps, op.twc)
-    op.npc = max(1, min(int(_os.environ.get("HGSFA_NPC", "8")), op.n_nodes // 32))
+        ps["SW"], ps["TW"], ps["KS"] = _pass_split(ps, op.twc, op.warps)
+    op.npc = max(1, min(8, op.n_nodes // 32))
     runs = [_gather_runs(g) for g in op.gather]
     op.n_runs = max(len(r) for r in runs)
     op.runs = np.zeros((op.n_nodes, op.n_runs, 4), dtype=np.int32)
@@ -591,7 +614,7 @@ def _fuse_id_pow(segs):
     return out
 
 
-FOLD_BIAS = float(_os.environ.get("HGSFA_FOLD_BIAS", "1.5"))
+FOLD_BIAS = float(_os.environ.get("HGSFA_FOLD_BIAS", "1.7"))
 FUSE_ID_POW = _os.environ.get("HGSFA_FUSE_ID_POW", "1") != "0"
 
 
@@ -782,7 +805,8 @@ def serialize(spec):
     for op in spec.ops:
         n_w = 1 if op.shared else op.n_nodes
         n_terms = sum(ps["K"] for ps in op.passes)
-        out.append(struct.pack("<12q", op.n_nodes, op.d_in, op.in_dim, op.out_dim, len(op.passes), int(op.shared),
+        out.append(struct.pack("<12q", op.n_nodes, op.d_in, op.in_dim, op.out_dim, len(op.passes),
+                               int(op.shared) | (op.warps << 8),
                                op.n_rows, op.twc, op.alg_flops, op.exe_flops, op.npc, op.n_runs)
                    + struct.pack("<2d", float(op.clip[0]), float(op.clip[1]))
                    + struct.pack("<2q", op.param_floats, n_terms))
@@ -838,7 +862,7 @@ def describe(spec):
     for k, op in enumerate(spec.ops):
         ps = ", ".join("K%d->N%d(%dx%d sw%d ks%d tw%d)" % (p["K_real"], p["N_real"], p["NT"], p["NTL"], p["SW"], p["KS"], p["TW"])
                        for p in op.passes)
-        lines.append("  op%-2d nodes=%-4d d_in=%-4d out=%-5d %s %s [%s] twc=%d npc=%d runs=%d rows=%d smem=%dK"
+        lines.append("  op%-2d nodes=%-4d d_in=%-4d out=%-5d %s %s [%s] warps=%d twc=%d runs=%d rows=%d smem=%dK"
                      % (k, op.n_nodes, op.d_in, op.out_dim, "clone" if op.shared else "layer", op.mode, ps,
-                        op.twc, op.npc, op.n_runs, op.n_rows, _op_smem(op, op.twc) // 1024))
+                        op.warps, op.twc, op.n_runs, op.n_rows, _op_smem(op, op.twc) // 1024))
     return "\n".join(lines)

@@ -95,3 +95,27 @@ def test_node_facades(tiny_flow):
     part = g.execute(x, nodenr=1)
     assert np.abs(part - onodes.flow_execute(tiny_flow, x, nodenr=1)).max() < 1e-2
     g.close()
+
+
+@pytest.mark.parametrize("n,dim", [(1, 16), (128, 128), (300, 144), (1000, 4096), (77, 200)])
+def test_tile_windows_layout(n, dim):
+    """row-major (n, dim) uint8 -> TILED [tile][feature][128] (include/hgsfa.h), padding windows zero."""
+    import ctypes as C
+    import torch
+    from pyfaceanalysis_b200 import _lib
+    rng = np.random.default_rng(n * 7 + dim)
+    x = rng.integers(0, 256, (n, dim), dtype=np.uint8)
+    tiles = (n + 127) // 128
+    ref = np.zeros((tiles, dim, 128), dtype=np.uint8)
+    for t in range(tiles):
+        blk = x[t * 128:(t + 1) * 128]
+        ref[t, :, :len(blk)] = blk.T
+    for ld_pad in (0, 16, 3):                       # aligned fast path, aligned with padding, unaligned fallback
+        xp = np.zeros((n, dim + ld_pad), dtype=np.uint8)
+        xp[:, :dim] = x
+        d_x = torch.as_tensor(xp, device="cuda:0")
+        d_y = torch.full((tiles * dim * 128,), 255, dtype=torch.uint8, device="cuda:0")
+        _lib.check(_lib.load().hgsfa_tile_windows_device(C.c_void_p(d_x.data_ptr()), _lib.U8, n, dim, dim + ld_pad,
+                                                         C.c_void_p(d_y.data_ptr()), _lib.U8, None))
+        torch.cuda.synchronize()
+        assert np.array_equal(d_y.cpu().numpy().reshape(tiles, dim, 128), ref), (n, dim, ld_pad)
