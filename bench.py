@@ -67,6 +67,16 @@ def _fp32_peak():
         return 74.4, "nominal 148 SM x 128 FMA x 2 x 1.965 GHz"
 
 
+def _traffic_per_window():
+    """DRAM bytes per window of the layer kernels, from the committed ncu launch list (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+            t = json.load(f)
+        return float(t["layer_dram_bytes_per_window"]), t["source"], float(t["layer_share_of_step"])
+    except Exception:
+        return None, None, None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -288,6 +298,7 @@ def main():
         fp32_peak, fp32_src = _fp32_peak()
         peaks = _peaks()
         achieved_tflops = fl["algorithmic"] / (kernel_ms_last * 1e-3) / 1e12 if kernel_ms_last > 0 else None
+        tpw, tsrc, lshare = _traffic_per_window()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -303,7 +314,10 @@ def main():
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": (achieved_tflops / fp32_peak) if achieved_tflops else None, "traffic": None,
+                         "frac": (achieved_tflops / fp32_peak) if achieved_tflops else None,
+                         "traffic": (tpw * n) if tpw else None, "traffic_unit": "bytes per step (all layer launches)",
+                         "traffic_source": tsrc, "kernel_share_of_step_ncu": lshare,
+                         "algorithmic_bytes_per_step": fl["min_bytes"],
                          "kernel": "hgsfa::layer_kernel (all 11 layer launches of a step)",
                          "algorithmic_flops_per_window": fl["algorithmic"] / n,
                          "executed_flops_per_window": fl["executed"] / n,

@@ -144,11 +144,14 @@ static size_t layout_op(OpDev& d, int scratch_floats, int el, int* nstages_out) 
   d.sm_stage0 = (int)off;
   d.sm_stage_bytes = (int)stage;
   d.sm_raw_bytes = (int)raw;
+  // stages: as many as fit in the CTA's share of shared memory (two 4-warp CTAs per SM, or one 8-warp CTA);
+  // ops with a CTA-wide barrier per pass gain nothing beyond two
   const size_t limit = 227 * 1024;
-  int ns = (off + 2 * stage <= limit && d.npc > 1) ? 2 : 1;
-  // two stages only pay when they do not cost the second resident CTA
-  if (ns == 2 && off + 2 * stage > 113 * 1024 && off + stage <= 113 * 1024) ns = 1;
-  if (off + ns * stage > limit) return 0;
+  const size_t budget = (d.warps == 4) ? (limit / 2 - 1024) : limit;
+  const int max_stages = d.simple ? 4 : 2;
+  int ns = 1;
+  while (ns < max_stages && ns < d.npc && off + size_t(ns + 1) * stage <= budget) ++ns;
+  if (off + size_t(ns) * stage > limit) return 0;
   d.nstages = ns;
   *nstages_out = ns;
   return off + ns * stage;
@@ -360,9 +363,12 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       if (dp.KS > 1) op.scratch_floats = std::max(op.scratch_floats, (d.warps / 2) * dp.SW * dp.NT * TILE);
     }
     if (!cur.ok) break;
+    // barrier-free hand-over of stages for one-pass, no-K-split ops: measured equal to the per-node barrier on
+    // B200 (profiles/README_r01.md), so it stays opt-in
+    d.simple = (getenv("HGSFA_SIMPLE") && d.n_passes == 1 && d.pass[0].KS == 1) ? 1 : 0;
     for (int v = 0; v < 2; ++v) {
       OpDev tmp = d;
-      tmp.npc = 2;   // worst case for the reservation: two stages whenever they fit
+      tmp.npc = 64;   // worst case for the reservation: as many stages as ever fit
       op.smem_bytes[v] = layout_op(tmp, op.scratch_floats, v ? 1 : 4, &op.nstages[v]);
     }
     if (op.smem_bytes[0] == 0)

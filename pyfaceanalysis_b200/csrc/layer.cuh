@@ -56,7 +56,7 @@ struct PassDev {
 
 struct OpDev {
   int n_nodes, d_in, in_dim, out_dim, n_passes, shared, n_rows, twc;
-  int npc, n_runs, nstages, param_floats, n_terms, warps;
+  int npc, n_runs, nstages, param_floats, n_terms, warps, simple;
   float clip_lo, clip_hi;
   const Run* runs;        // [n_nodes][n_runs]
   const int* out_col;     // [n_nodes]
@@ -533,17 +533,22 @@ template <typename IN_T, int NTMAX>
 __global__ void __launch_bounds__(THREADS, (NTMAX <= 16 ? 2 : 1))
     layer_kernel(const OpDev op, const IN_T* __restrict__ xin, float* __restrict__ xout, int64_t ntiles) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [2]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [4] "stage filled" mbarriers
+  int* released = reinterpret_cast<int*>(smem + 64);           // [4] warps done with a stage (simple ops)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nwarps = blockDim.x >> 5;
   const int64_t tile0 = int64_t(blockIdx.x) * op.twc;
   const int node_begin = blockIdx.y * op.npc;
   const int node_end = min(op.n_nodes, node_begin + op.npc);
   const int64_t tiles_left = ntiles - tile0;
   const int valid_tiles = tiles_left < op.twc ? (int)tiles_left : op.twc;
+  const int nst = op.nstages;
 
   if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&full[i], 1);
+      released[i] = 0;
+    }
     mbar_fence_init();
   }
   {  // term table of all passes (shared by every node of the op)
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(THREADS, (NTMAX <= 16 ? 2 : 1))
   }
   __syncthreads();
 
-  // producer: bulk copies of one node's receptive field (valid tile slots) + parameter block
+  // producer (any one warp): bulk copies of one node's receptive field (valid tile slots) + parameter block
   auto issue = [&](int node, int s) {
     uint8_t* stage = smem + op.sm_stage0 + size_t(s) * op.sm_stage_bytes;
     const Run* runs = op.runs + size_t(node) * op.n_runs;
@@ -579,13 +584,13 @@ __global__ void __launch_bounds__(THREADS, (NTMAX <= 16 ? 2 : 1))
     }
   };
 
-  if (warp == 0 && node_begin < node_end) issue(node_begin, 0);
+  if (warp == 0)
+    for (int i = 0; i < nst && node_begin + i < node_end; ++i) issue(node_begin + i, i);
+
   int it = 0;
   for (int node = node_begin; node < node_end; ++node, ++it) {
-    const int s = (op.nstages == 2) ? (it & 1) : 0;
-    const uint32_t parity = (op.nstages == 2) ? ((it >> 1) & 1) : (it & 1);
-    if (op.nstages == 2 && warp == 0 && node + 1 < node_end) issue(node + 1, s ^ 1);
-    mbar_wait(&full[s], parity);
+    const int s = it % nst;
+    mbar_wait(&full[s], uint32_t(it / nst) & 1u);
     const uint8_t* stage = smem + op.sm_stage0 + size_t(s) * op.sm_stage_bytes;
 #pragma unroll 1
     for (int p = 0; p < op.n_passes; ++p) {
@@ -600,9 +605,28 @@ __global__ void __launch_bounds__(THREADS, (NTMAX <= 16 ? 2 : 1))
         case 32 * 4 + 1: if constexpr (NTMAX >= 32) run_pass<IN_T, 32, 1>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
         default: break;
       }
-      __syncthreads();   // shared rows of this pass visible; stage fully consumed after the last pass
+      if (!op.simple) __syncthreads();   // shared rows of this pass visible; stage consumed after the last pass
     }
-    if (op.nstages == 1 && warp == 0 && node + 1 < node_end) issue(node + 1, 0);
+    // ---- hand the stage back.  Simple ops (one pass, no K-split) have no CTA-wide barrier at all: warps
+    // drift apart by up to nst nodes, and the LAST warp to leave a stage refills it for node + nst.
+    if (op.simple) {
+      int last = 0;
+      __syncwarp();
+      if (lane == 0) {
+        const int old = atomicAdd(&released[s], 1);
+        if (old == nwarps - 1) {
+          released[s] = 0;
+          last = 1;
+        }
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last && node + nst < node_end) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(node + nst, s);
+      }
+    } else if (warp == 0 && node + nst < node_end) {
+      issue(node + nst, s);
+    }
   }
 }
 

@@ -383,17 +383,21 @@ class OpSpec(object):
         self.clip = (-np.inf, np.inf)   # saturation applied when results are stored to the output buffer
 
 
+WIDE_TILES = __import__("os").environ.get("HGSFA_WIDE_TILES", "0") != "0"   # measured: no gain on U11L_64 (profiles/README_r01.md)
+
+
 def _choose_tile(n_real):
     """(NT, NTL): columns per warp register tile and number of column tiles, NT * NTL >= n_real.
 
-    Minimises padded columns; on ties prefers NT <= 16 (register footprint that keeps two CTAs per SM),
-    then the larger NT (fewer shared-memory reads per FMA)."""
+    Minimises padded columns; on ties prefers fewer, wider column tiles: every column tile of a node is a
+    different warp that re-evaluates the expansion (MUFU work scales with NTL), and a wider tile amortises the
+    operand conversion over more FMAs."""
     best = None
     for ntl in (1, 2, 4):
         for nt in (8, 16, 24, 32):
             if nt * ntl < n_real:
                 continue
-            key = (nt * ntl, nt > 16, -nt)
+            key = (nt * ntl, ntl) if WIDE_TILES else (nt * ntl, nt > 16, -nt)
             if best is None or key < best[0]:
                 best = (key, nt, ntl)
     if best is None:
@@ -690,7 +694,17 @@ def compile_flow(flow, input_dim=None, igsfa_mode="auto"):
         if not pending_layers:
             return
         fields, gathers = pending_layers
-        op = _assemble_layer(fields, gathers, buf_dim, igsfa_mode)
+        try:
+            op = _assemble_layer(fields, gathers, buf_dim, igsfa_mode)
+        except UnsupportedFlow as first:
+            # a folded iGSFA pass carries a D x out weight block; when that (plus the receptive field) exceeds
+            # shared memory the two-pass form (D x J and (d+J) x P blocks) may still fit
+            if igsfa_mode != "auto":
+                raise
+            try:
+                op = _assemble_layer(fields, gathers, buf_dim, "two_pass")
+            except UnsupportedFlow:
+                raise first
         spec.ops.append(op)
         buf_dim = op.out_dim
         cols = np.arange(buf_dim, dtype=np.int64)

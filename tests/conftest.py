@@ -80,3 +80,9 @@ def class_samples(clf, n_per_class, rng, spread=1.0):
         cov = (cov + cov.T) / 2
         xs.append(rng.multivariate_normal(mu, cov * spread, size=n_per_class, method="eigh"))
     return np.concatenate(xs, axis=0)
+
+
+@pytest.fixture(scope="session")
+def u11l96_flow():
+    from pyfaceanalysis_b200 import synthetic
+    return synthetic.cached_flow("U11L_96", seed=1, n_train=1500)

@@ -119,3 +119,35 @@ def test_tile_windows_layout(n, dim):
                                                          C.c_void_p(d_y.data_ptr()), _lib.U8, None))
         torch.cuda.synchronize()
         assert np.array_equal(d_y.cpu().numpy().reshape(tiles, dim, 128), ref), (n, dim, ld_pad)
+
+
+def test_age_like_96x96_flow_and_real_heads(u11l96_flow, classifiers):
+    """BASELINE config 4 shape: 96x96 crops (9216 inputs), overlapping 6x6 / stride-3 fields, 3-wide joins,
+    receptive fields up to 180 inputs (forces the two-pass iGSFA form), then the REAL shipped age / race /
+    gender heads (4x39, 5x2, 5x2) on the first features."""
+    from pyfaceanalysis_b200 import GpuFlow, GpuGaussianClassifier, synthetic
+    from oracle import gauss as ogauss
+    g = GpuFlow(u11l96_flow)
+    assert g.input_dim == 9216
+    x = synthetic.synthetic_patches(260, (96, 96), 31)
+    y = g.execute(x)
+    ref = onodes.flow_execute(u11l96_flow, x.astype(np.float64))
+    err = np.abs(y - ref) / u11l96_flow._train_output_std
+    assert err.max() <= TOL, err.max()
+    heads = [c for c in classifiers if "Generalize" in c.name]
+    assert sorted((c.input_dim, len(c.p)) for c in heads) == [(4, 39), (5, 2), (5, 2)]
+    for clf in heads:
+        h = GpuGaussianClassifier(clf)
+        D = h.input_dim
+        # the synthetic features are not the distribution these heads were fitted on: map them onto the head's
+        # class means so that the comparison exercises finite posteriors as well as the NaN regime
+        feats = np.asarray(clf.means)[np.arange(len(y)) % len(clf.means)] + y[:, :D] * 0.05
+        got = h.regression(feats.astype(np.float32), clf.avg_labels, estimate_std=(D == 4))
+        exp = ogauss.regression(clf, feats.astype(np.float32).astype(np.float64), clf.avg_labels, estimate_std=(D == 4))
+        if D == 4:
+            assert np.allclose(got[0], exp[0], rtol=1e-9, atol=1e-9, equal_nan=True)
+            assert np.allclose(got[1], exp[1], rtol=1e-7, atol=1e-7, equal_nan=True)
+        else:
+            assert np.allclose(got, exp, rtol=1e-9, atol=1e-9, equal_nan=True)
+        h.close()
+    g.close()
