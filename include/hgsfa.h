@@ -123,6 +123,13 @@ int hgsfa_crop_extent_batch_device(const uint8_t* const* d_img_ptrs, const int32
                                    const double* d_angles, int64_t n, int ow, int oh, int filter,
                                    void* d_out, int out_dtype, int out_layout, void* stream);
 
+/* Per-patch contrast normalisation of TILED float32 patches, in place: the
+ * contrast_enhance="AgeContrastEnhancement_Avg_Std", obj_avg, obj_std arguments of cuicuilco's
+ * extract_subimages_rotate as the eye stage passes them (face_analysis.py:1042-1045):
+ * v = x / 255;  y = (v - mean(v)) / (std(v) + 1e-8) * obj_std + obj_avg   (definition: oracle/crop.py). */
+int hgsfa_contrast_avg_std_device(float* d_patches_tiled, int64_t n, int64_t dim, double obj_avg,
+                                  double obj_std, void* stream);
+
 /* row-major <-> tiled conversion of a window matrix on the device (u8 or f32 elements) */
 int hgsfa_tile_windows_device(const void* d_src, int dtype, int64_t n, int64_t dim, int64_t ld,
                               void* d_dst_tiled, int dst_dtype, void* stream);

@@ -3,9 +3,13 @@
 Follows ``FaceDetectUpdated.py:589-761`` statement by statement (per sampling value: grid, stage loop with
 the skip rules of ``:674-682``, regression, coordinate update, discard mask, boolean compaction of coords /
 angles / indices / sl / subimages_arr / confidence) using the oracle's own crop, flow, head and controller.
-After the stage loop the reference refines the eyes with the eye networks (``:946-1041``); like the product
- this oracle stops at the approximate eye positions of
-``compute_approximate_eye_boxes_coordinates`` (``face_analysis.py:61-135``) and then purges (``:1180``).
+After the stage loop the eyes are refined with the eye networks (``FaceDetectUpdated.py:946-1041`` ->
+``find_Left_Right_eyes``, ``face_analysis.py:1036-1109``) when they are supplied, otherwise the approximate eye
+positions of ``compute_approximate_eye_boxes_coordinates`` (``face_analysis.py:61-135``) are kept; then the purge
+(``:1180``).  The age / race / gender stage (``face_analysis.py:1170-1306``) is not restated.
+
+``curr_confidence`` is compacted at every stage here; the reference only re-assigns it at Disc stages
+(``FaceDetectUpdated.py:758-759``), which is equivalent because the last face stage is a Disc.
 """
 import numpy as np
 
@@ -18,9 +22,37 @@ from . import nodes as onodes
 CUT_OFFS_FACE = [0.99, 0.95, 0.85, 0.8, 0.7, 0.6, 0.5, 0.45, 0.10, 0.05]
 
 
+def find_eyes(image, curr_angles, eyes_box_orig, eye_header, eye_net, clf_x, clf_y, interpolation=ocrop.NEAREST,
+              flow_execute=onodes.flow_execute, regression=ogauss.regression, tolerance_xy_eye=9.0):
+    """``find_Left_Right_eyes`` with left_eye=1 (both eyes go through it unmirrored, ``face_analysis.py:1022-1033``)."""
+    _, _, _, _, ew, eh, erw, erh = eye_header
+    box = eyes_box_orig.copy()
+    too_far = np.zeros(len(box), dtype=bool)
+    if len(box) == 0:
+        return box, too_far
+    patches = ocrop.extract_subimages(image, box, curr_angles, (ew, eh), interpolation)
+    patches = ocrop.contrast_avg_std(patches, 0.11, 0.15)
+    sl = flow_execute(eye_net, patches)          # the reference executes the same flow once per label
+    reg_x = regression(clf_x, sl[:, 0:clf_x.input_dim], clf_x.avg_labels)
+    reg_y = regression(clf_y, sl[:, 0:clf_y.input_dim], clf_y.avg_labels)
+    with np.errstate(invalid="ignore"):
+        too_far |= np.abs(reg_x) >= tolerance_xy_eye
+        too_far |= np.abs(reg_y) >= tolerance_xy_eye
+    reg_out_x = (reg_x / 2.3719) * np.abs(box[:, 2] - box[:, 0]) / erw
+    reg_out_y = (reg_y / 2.3719) * np.abs(box[:, 3] - box[:, 1]) / erh
+    rot = -1 * 1 * curr_angles * np.pi / 180
+    dx = reg_out_x * np.cos(rot) - reg_out_y * np.sin(rot)
+    dy = reg_out_y * np.cos(rot) + reg_out_x * np.sin(rot)
+    box[:, 0] = box[:, 0] - 1 * dx
+    box[:, 2] = box[:, 2] - 1 * dx
+    box[:, 1] = box[:, 1] - dy
+    box[:, 3] = box[:, 3] - dy
+    return box, too_far
+
+
 def detect_image(image, header, network_types, networks, classifiers, smallest_face, num_face_stages,
                  cut_offs_face=CUT_OFFS_FACE, tol_posxy=1.1, tol_scale=1.1, tol_angle=1.1, interpolation=ocrop.NEAREST,
-                 flow_execute=onodes.flow_execute, regression=ogauss.regression):
+                 flow_execute=onodes.flow_execute, regression=ogauss.regression, eye_header=None):
     net_Dx, net_Dy, net_Dang, net_mins, net_maxs, sw, sh, rw, rh = header
     im_height, im_width = image.shape
     stage_counts = np.zeros(num_face_stages, dtype=np.int64)
@@ -73,10 +105,31 @@ def detect_image(image, header, network_types, networks, classifiers, smallest_f
                 curr_confidence = reg_out[keep].copy()
             else:
                 curr_confidence = curr_confidence[keep].copy()
+        n_face = len(curr_coords)
+        eyes_orig = np.zeros((n_face, 4))
+        eyesL_box_orig = np.zeros((n_face, 4))
+        eyesR_box_orig = np.zeros((n_face, 4))
+        for i, box in enumerate(curr_coords):
+            eyes_orig[i], eyesL_box_orig[i], eyesR_box_orig[i] = ctl.eye_boxes(box, rot_angle=curr_angles[i])
+        eye_net = networks[num_face_stages] if eye_header is not None and len(networks) > num_face_stages else None
+        if eye_net is not None:
+            cx, cy = classifiers[num_face_stages], classifiers[num_face_stages + 1]
+            eyesL_box, farL = find_eyes(image, curr_angles, eyesL_box_orig, eye_header, eye_net, cx, cy, interpolation,
+                                        flow_execute, regression)
+            eyesR_box, farR = find_eyes(image, curr_angles, eyesR_box_orig, eye_header, eye_net, cx, cy, interpolation,
+                                        flow_execute, regression)
+            too_far = farL | farR
+            eyesL = (eyesL_box[:, 0:2] + eyesL_box[:, 2:4]) / 2.0
+            eyesR = (eyesR_box[:, 0:2] + eyesR_box[:, 2:4]) / 2.0
+            eyesL, eyesR = eyesL[too_far == 0], eyesR[too_far == 0]
+            curr_coords, curr_angles = curr_coords[too_far == 0, :], curr_angles[too_far == 0]
+            # reference quirk kept: curr_confidence is NOT filtered by eye_xy_too_far (FaceDetectUpdated.py:1011-1017),
+            # so face j of the survivors reports the confidence of face j of the pre-eye-stage list (:1036-1041)
+        else:
+            eyesL, eyesR = eyes_orig[:, 0:2], eyes_orig[:, 2:4]
         for j, box in enumerate(curr_coords):
-            eyes, _, _ = ctl.eye_boxes(box, rot_angle=curr_angles[j])
-            detections.append(np.array([box[0], box[1], box[2], box[3], curr_angles[j], eyes[0], eyes[1], eyes[2],
-                                        eyes[3], curr_confidence[j]]))
+            detections.append(np.array([box[0], box[1], box[2], box[3], curr_angles[j], eyesL[j][0], eyesL[j][1],
+                                        eyesR[j][0], eyesR[j][1], curr_confidence[j]]))
     raw = np.array(detections).reshape(-1, 10)
     purged = np.array(ctl.purge(detections)).reshape(-1, 10) if len(detections) else np.zeros((0, 10))
     return purged, dict(stage_counts=stage_counts, raw=raw)

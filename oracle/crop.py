@@ -137,3 +137,13 @@ def extract_subimages(img, coords, angles=None, out_size=(64, 64), interpolation
             p = extent_rotated(img, coords[k], -ang, out_size, bilinear=(interpolation == BILINEAR))
         out[k] = p.reshape(-1)
     return out
+
+
+def contrast_avg_std(patches, obj_avg, obj_std):
+    """cuicuilco ``contrast_enhance="AgeContrastEnhancement_Avg_Std"`` (``face_analysis.py:1042-1045, 1238``).
+    The cuicuilco source is unavailable -- PARITY UNPINNED; defined here per patch as
+    ``v = x / 255; y = (v - mean(v)) / (std(v) + 1e-8) * obj_std + obj_avg`` (float, unclipped)."""
+    v = np.asarray(patches, dtype=np.float64) / 255.0
+    m = v.mean(axis=1, keepdims=True)
+    sd = v.std(axis=1, keepdims=True)
+    return (v - m) / (sd + 1e-8) * obj_std + obj_avg

@@ -12,9 +12,14 @@ kernels of ``libhgsfa.so``, and the only per-stage host round trip is the 8-byte
 are independent until the per-image purge, so batching changes nothing but the order of evaluation; the
 stable compaction keeps the reference's order (image, scale, window) inside the batch.
 
-What is NOT here yet: the eye-refinement stages (EyeLX / EyeLY need cuicuilco's
-"AgeContrastEnhancement_Avg_Std" patch normalisation) and the age / race / gender stage; detections carry
-the approximate eye positions of ``compute_approximate_eye_boxes_coordinates``.
+After the face stages the eyes of every surviving face are refined with the eye network and its two heads
+(``FaceDetectUpdated.py:946-1041`` -> ``find_Left_Right_eyes``, ``face_analysis.py:1036-1109``): rotated 64x64 crops
+of the two eye boxes, per-patch contrast normalisation ("AgeContrastEnhancement_Avg_Std", obj_avg 0.11, obj_std
+0.15 -- definition in oracle/crop.py), one execution of the eye flow per eye (the reference runs it once per label
+on the same input), EyeLX / EyeLY regressions, |reg| >= 9 discards the face.  Without eye networks the detections
+carry the approximate eye positions of ``compute_approximate_eye_boxes_coordinates``.
+
+What is NOT here yet: the age / race / gender stage (``normalize_image`` needs BICUBIC resampling).
 """
 from __future__ import annotations
 
@@ -42,6 +47,18 @@ def approximate_eye_coordinates(boxes, angles):
     el_dx = (-1 * eye_dx) * np.cos(rad) - eye_dy * np.sin(rad)
     el_dy = eye_dy * np.cos(rad) + (-1 * eye_dx) * np.sin(rad)
     return np.stack([fc_x + el_dx, fc_y - el_dy, fc_x + er_dx, fc_y - er_dy], axis=1)
+
+
+def approximate_eye_boxes(boxes, angles):
+    """Eye centres plus the left / right eye boxes of ``compute_approximate_eye_boxes_coordinates``:
+    returns (eyes (N,4), left boxes (N,4), right boxes (N,4))."""
+    eyes = approximate_eye_coordinates(boxes, angles)
+    bw = (np.abs(boxes[:, 2] - boxes[:, 0]) / (64.0 * 2 * 0.825)) * (64 * 2.3719 / 2)
+    bh = bw + 0.0
+
+    def box(cx, cy):
+        return np.stack([cx - bw / 2.0, cy - bh / 2.0, cx + bw / 2.0, cy + bh / 2.0], axis=1)
+    return eyes, box(eyes[:, 0], eyes[:, 1]), box(eyes[:, 2], eyes[:, 3])
 
 
 def purge_detections(det, weight_confidences_by_area=True):
@@ -85,7 +102,7 @@ class FaceDetector(object):
     """
 
     def __init__(self, header_net, network_types, networks, classifiers, num_face_stages=None,
-                 cut_offs_face=None, interpolation=_lib.NEAREST, device=0, **overrides):
+                 cut_offs_face=None, interpolation=_lib.NEAREST, device=0, header_eye=None, **overrides):
         import torch
         self.torch = torch
         self.header = tuple(header_net)
@@ -102,6 +119,12 @@ class FaceDetector(object):
         if self.networks and self.networks[0] is None:
             raise ValueError("the first stage needs a network")
         self._labels = {}
+        # eye stage: network_types[n_stages] = EyeLX, [n_stages + 1] = EyeLY (same flow file, two heads)
+        self.header_eye = tuple(header_eye) if header_eye is not None else None
+        self.eye_net = None
+        if self.header_eye is not None and len(networks) > n_stages and networks[n_stages] is not None:
+            self.eye_net = networks[n_stages]
+            self.eye_clf_x, self.eye_clf_y = classifiers[n_stages], classifiers[n_stages + 1]
 
     # ------------------------------------------------------------------------------------------
     def _labels_dev(self, clf):
@@ -110,6 +133,48 @@ class FaceDetector(object):
             t = self.torch.as_tensor(np.ascontiguousarray(clf.avg_labels, dtype=np.float64), device=self.dev)
             self._labels[id(clf)] = t
         return t
+
+    def _regress(self, clf, sl, n, sp):
+        """classifiers[i].regression(sl[:, 0:D], avg_labels) on device tensors -> float64 tensor (n,)."""
+        torch = self.torch
+        if sl.shape[1] < clf.input_dim:
+            raise ValueError("x has dimension %d, should be %d" % (sl.shape[1], clf.input_dim))
+        reg = torch.empty(n, dtype=torch.float64, device=self.dev)
+        _lib.check(_lib.load().hgsfa_gauss_regress_device(
+            clf.handle, C.c_void_p(sl.data_ptr()), _lib.F32, n, sl.stride(0), C.c_void_p(self._labels_dev(clf).data_ptr()),
+            C.c_void_p(reg.data_ptr()), None, None, None, sp))
+        return reg
+
+    def _find_eyes(self, img_ptrs, img_hw, img_idx, angles_dev, angles_h, eye_boxes_h, sp):
+        """``find_Left_Right_eyes`` (left_eye=1) for one eye of every surviving face."""
+        torch = self.torch
+        lib = _lib.load()
+        _, _, _, _, ew, eh, erw, erh = self.header_eye
+        n = len(eye_boxes_h)
+        boxes = torch.as_tensor(np.ascontiguousarray(eye_boxes_h), device=self.dev)
+        n_pad = (n + _lib.TILE - 1) // _lib.TILE * _lib.TILE
+        patches = torch.empty(n_pad * ew * eh, dtype=torch.float32, device=self.dev)
+        _lib.check(lib.hgsfa_crop_extent_batch_device(
+            C.c_void_p(img_ptrs.data_ptr()), C.c_void_p(img_hw.data_ptr()), C.c_void_p(img_idx.data_ptr()),
+            C.c_void_p(boxes.data_ptr()), C.c_void_p(angles_dev.data_ptr()), n, ew, eh, self.interpolation,
+            C.c_void_p(patches.data_ptr()), _lib.F32, _lib.TILED, sp))
+        _lib.check(lib.hgsfa_contrast_avg_std_device(C.c_void_p(patches.data_ptr()), n, ew * eh, 0.11, 0.15, sp))
+        sl = self.eye_net.execute_torch(patches, layout=_lib.TILED, n=n)
+        reg_x = self._regress(self.eye_clf_x, sl, n, sp).cpu().numpy()
+        reg_y = self._regress(self.eye_clf_y, sl, n, sp).cpu().numpy()
+        box = eye_boxes_h.copy()
+        with np.errstate(invalid="ignore"):
+            too_far = (np.abs(reg_x) >= 9.0) | (np.abs(reg_y) >= 9.0)
+        reg_out_x = (reg_x / 2.3719) * np.abs(box[:, 2] - box[:, 0]) / erw
+        reg_out_y = (reg_y / 2.3719) * np.abs(box[:, 3] - box[:, 1]) / erh
+        rot = -1 * 1 * angles_h * np.pi / 180
+        dx = reg_out_x * np.cos(rot) - reg_out_y * np.sin(rot)
+        dy = reg_out_y * np.cos(rot) + reg_out_x * np.sin(rot)
+        box[:, 0] = box[:, 0] - 1 * dx
+        box[:, 2] = box[:, 2] - 1 * dx
+        box[:, 1] = box[:, 1] - dy
+        box[:, 3] = box[:, 3] - dy
+        return box, too_far
 
     def detect(self, images, smallest_face=0.2, return_trace=False):
         """images: list of 2-D uint8 arrays (the reference's mode-'L' image, already prescaled).
@@ -134,6 +199,7 @@ class FaceDetector(object):
         coords_h = np.concatenate([p["coords"] for p in pyr])
         wh_h = np.concatenate([p["patch_wh"] for p in pyr])
         img_h = np.concatenate([np.full(len(p["coords"]), k, dtype=np.int32) for k, p in enumerate(pyr)])
+        scale_h = np.concatenate([p["scale"] for p in pyr])
 
         imgs_dev = [torch.as_tensor(np.ascontiguousarray(im, dtype=np.uint8), device=dev) for im in images]
         img_ptrs = torch.tensor([t.data_ptr() for t in imgs_dev], dtype=torch.int64, device=dev)
@@ -208,12 +274,37 @@ class FaceDetector(object):
                 sl = gather(sl.contiguous(), sl.shape[1] * 4)
                 n = n_new
 
-        # ---- survivors -> detections (host: dozens of rows) ----
+        # ---- survivors -> eyes -> detections (host arithmetic on dozens of rows, device compute for the eye flow) ----
         boxes = coords[:n].cpu().numpy()
         ang = angles[:n].cpu().numpy()
         im_of = img_idx[:n].cpu().numpy()
         cf = conf[:n].cpu().numpy()
-        eyes = approximate_eye_coordinates(boxes, ang) if n else np.zeros((0, 4))
+        scale_of = scale_h[orig_idx[:n].cpu().numpy()] if n else np.zeros(0, dtype=np.int32)
+        if n and self.eye_net is not None:
+            _, boxL, boxR = approximate_eye_boxes(boxes, ang)
+            eyesL_box, farL = self._find_eyes(img_ptrs, img_hw, img_idx[:n].contiguous(), angles[:n].contiguous(), ang, boxL, sp)
+            eyesR_box, farR = self._find_eyes(img_ptrs, img_hw, img_idx[:n].contiguous(), angles[:n].contiguous(), ang, boxR, sp)
+            ok = ~(farL | farR)
+            eyes = np.concatenate([(eyesL_box[:, 0:2] + eyesL_box[:, 2:4]) / 2.0,
+                                   (eyesR_box[:, 0:2] + eyesR_box[:, 2:4]) / 2.0], axis=1)[ok]
+            # reference quirk kept (FaceDetectUpdated.py:1011-1017, 1036-1041): curr_confidence is not filtered by
+            # eye_xy_too_far, so survivor j of a (scale, image) group reports the confidence of that group's face j
+            cf_out = np.empty(int(ok.sum()))
+            pos = 0
+            grp = np.stack([im_of, scale_of], axis=1)
+            start = 0
+            while start < n:
+                stop = start
+                while stop < n and (grp[stop] == grp[start]).all():
+                    stop += 1
+                k_ok = int(ok[start:stop].sum())
+                cf_out[pos:pos + k_ok] = cf[start:start + k_ok]
+                pos += k_ok
+                start = stop
+            boxes, ang, im_of, cf = boxes[ok], ang[ok], im_of[ok], cf_out
+            n = len(boxes)
+        else:
+            eyes = approximate_eye_coordinates(boxes, ang) if n else np.zeros((0, 4))
         raw = np.concatenate([boxes, ang[:, None], eyes, cf[:, None]], axis=1) if n else np.zeros((0, 10))
         per_image_raw = [raw[im_of == k] for k in range(len(images))]
         result = [purge_detections(r) if len(r) else np.zeros((0, 10)) for r in per_image_raw]

@@ -183,6 +183,37 @@ __global__ void __launch_bounds__(256) crop_gather_kernel(const uint8_t* img, in
   }
 }
 
+// Per-patch contrast normalisation of TILED float patches, in place (cuicuilco's
+// "AgeContrastEnhancement_Avg_Std" as defined by oracle/crop.py: v = x / 255;
+// y = (v - mean(v)) / (std(v) + 1e-8) * obj_std + obj_avg).  A lane owns one window: every load of a
+// warp is 128 contiguous bytes of one pixel row of the tile; statistics are accumulated in double.
+__global__ void __launch_bounds__(128) contrast_avg_std_kernel(float* __restrict__ x, int64_t n, int64_t dim,
+                                                               double obj_avg, double obj_std) {
+  const int64_t tile = blockIdx.x;
+  const int w = threadIdx.x;
+  if (tile * TILE_W + w >= n) return;
+  float* p = x + size_t(tile) * dim * TILE_W + w;
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t f = 0; f < dim; ++f) {
+    const double v = double(p[f * TILE_W]) / 255.0;
+    s1 += v;
+    s2 = fma(v, v, s2);
+  }
+  const double mean = s1 / double(dim);
+  // population variance like numpy.std; second pass for the same rounding behaviour as (v - mean) ** 2
+  double var = 0.0;
+  for (int64_t f = 0; f < dim; ++f) {
+    const double d = double(p[f * TILE_W]) / 255.0 - mean;
+    var = fma(d, d, var);
+  }
+  (void)s2;
+  const double scale = obj_std / (sqrt(var / double(dim)) + 1e-8);
+  for (int64_t f = 0; f < dim; ++f) {
+    const double v = double(p[f * TILE_W]) / 255.0;
+    p[f * TILE_W] = float((v - mean) * scale + obj_avg);
+  }
+}
+
 struct CropScratch {
   DevBuf xtab, ytab;
 };
@@ -258,6 +289,17 @@ extern "C" int hgsfa_crop_extent_batch_device(const uint8_t* const* d_img_ptrs, 
   HG_CHECK((d_img_ptrs && d_img_hw && d_img_index) || n == 0, "hgsfa_crop_extent_batch: null image table");
   return crop_launch(nullptr, 1, 1, ImageTable{d_img_ptrs, d_img_hw, d_img_index}, d_boxes, d_angles, n, ow, oh, filter,
                      d_out, out_dtype, out_layout, stream);
+}
+
+extern "C" int hgsfa_contrast_avg_std_device(float* d_patches_tiled, int64_t n, int64_t dim, double obj_avg, double obj_std,
+                                             void* stream) {
+  HG_CHECK(n >= 0 && dim > 0, "hgsfa_contrast_avg_std: bad shape n=%lld dim=%lld", (long long)n, (long long)dim);
+  if (n == 0) return 0;
+  HG_CHECK(d_patches_tiled, "hgsfa_contrast_avg_std: null buffer");
+  contrast_avg_std_kernel<<<(unsigned)ceil_div(n, TILE_W), TILE_W, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_patches_tiled, n, dim, obj_avg, obj_std);
+  HG_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int hgsfa_crop_extent(const uint8_t* img, int H, int W, const double* boxes, const double* angles,

@@ -19,6 +19,7 @@ from pyfaceanalysis_b200 import pickles, synthetic
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = (40, 20, 22.5, 0.694, 0.981, 64, 64, 128, 128)     # Pipelines/Pipeline_experimental.txt:2
+HEADER_EYE = (8, 8, 0.675, 0.975, 64, 64, 64, 64)           # Pipelines/Pipeline_experimental.txt:3
 NETWORK_TYPES = ["Disc1", "PosX0", "PosY0", "PAng0", "Scale0", "Disc3", "PosX1", "PosY1", "PAng1", "Scale1",
                  "Disc5", "PosX2", "PosY2", "PAng2", "Scale2", "Disc7", "Disc9"]   # stages 0..16 of the pipeline
 
@@ -94,6 +95,31 @@ def training_set(n, rng, ranges):
     return np.asarray(patches[:n]), np.asarray(labels[:n])
 
 
+def eye_training_set(n, rng):
+    """Contrast-normalised 64x64 eye-box crops with known eye displacement (eye regression units: 64 = box)."""
+    from oracle import controller as octl
+    patches, labels = [], []
+    per_scene = 30
+    for s in range((n + per_scene - 1) // per_scene):
+        face = (rng.uniform(110, 210), rng.uniform(90, 150), rng.uniform(55, 85), rng.uniform(-8, 8))
+        img = render_scene(240, 320, [face], int(rng.integers(1 << 30)))
+        w = face[2] / 0.825
+        fbox = np.array([face[0] - w / 2, face[1] - w / 2, face[0] + w / 2, face[1] + w / 2])
+        _, boxL, boxR = octl.eye_boxes(fbox, rot_angle=face[3])
+        for _ in range(per_scene):
+            eb = (boxL if rng.random() < 0.5 else boxR).copy()
+            dx, dy = rng.uniform(-10, 10), rng.uniform(-10, 10)
+            bw = eb[2] - eb[0]
+            # displace the box so that the eye appears (dx, dy) regression pixels off-centre
+            sx, sy = dx * 2.3719 * bw / 64.0 / 2.3719, dy * 2.3719 * bw / 64.0 / 2.3719
+            eb[[0, 2]] += sx
+            eb[[1, 3]] += sy
+            p = ocrop.extract_subimages(img, eb[None, :], np.array([face[3]]))
+            patches.append(ocrop.contrast_avg_std(p, 0.11, 0.15)[0])
+            labels.append((dx, dy))
+    return np.asarray(patches[:n]), np.asarray(labels[:n])
+
+
 def fit_gaussian_classifier(feats, target, n_classes, lo, hi):
     """mdp.nodes.GaussianClassifier-shaped attribute bag: equal-width label bins, shared-ridge covariances."""
     edges = np.linspace(lo, hi, n_classes + 1)
@@ -162,14 +188,20 @@ def build_models(seed=0, spec="S5L_64", n_train=1600):
             first = kind == "PosX"
             networks.append((flows["pose0"] if serial == 0 else flows["pose1"]) if first else None)
             classifiers.append((h0 if serial == 0 else h1)[kind])
-    # 5 trailing placeholders (EyeLX, EyeLY, Age, Race, Gender) keep `num_networks - 5` meaningful
+    # eye stage: one flow, two heads (EyeLX 12 features, EyeLY 10 features like the shipped classifiers)
+    Pe, Le = eye_training_set(n_train // 2, rng)
+    eye_flow = synthetic.make_flow(spec, seed=seed + 5, train_patches=Pe, clip_sigmas=4.0)
+    Fe = onodes.flow_execute(eye_flow, Pe)
+    eye_x = fit_gaussian_classifier(Fe[:, :12], Le[:, 0], 25, -10.0, 10.0)
+    eye_y = fit_gaussian_classifier(Fe[:, :10], Le[:, 1], 25, -10.0, 10.0)
+    # 3 trailing placeholders (Age, Race, Gender) keep `num_networks - 5` meaningful
     types = NETWORK_TYPES + ["EyeLX", "EyeLY", "Age", "Race", "Gender"]
-    return dict(header=HEADER, network_types=types, networks=networks + [None] * 5, classifiers=classifiers + [None] * 5,
-                num_face_stages=len(NETWORK_TYPES))
+    return dict(header=HEADER, header_eye=HEADER_EYE, network_types=types, networks=networks + [eye_flow, eye_flow] + [None] * 3,
+                classifiers=classifiers + [eye_x, eye_y] + [None] * 3, num_face_stages=len(NETWORK_TYPES))
 
 
 def cached_models(seed=0, spec="S5L_64"):
-    path = os.path.join(ROOT, "build", "flows", "cascade_%s_%d_v2.pckl" % (spec, seed))
+    path = os.path.join(ROOT, "build", "flows", "cascade_%s_%d_v3.pckl" % (spec, seed))
     if os.path.exists(path):
         with open(path, "rb") as f:
             return pickles.loads(f.read())

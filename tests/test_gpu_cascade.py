@@ -112,7 +112,8 @@ def test_batched_cascade_matches_reference_loop():
     nets, clfs = _gpu_models(m)
     gpu_flow = {id(f): g for f, g in zip(m["networks"], nets) if f is not None}
     gpu_head = {id(c): g for c, g in zip(m["classifiers"], clfs) if c is not None}
-    det = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=CUT)
+    det = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=CUT, header_eye=m["header_eye"])
+    assert det.eye_net is not None
     images = [cm.test_scene(seed)[0] for seed in (5, 6, 7)]
     got, trace = det.detect(images, smallest_face=0.2, return_trace=True)
     ref_counts = np.zeros(m["num_face_stages"], dtype=np.int64)
@@ -121,16 +122,21 @@ def test_batched_cascade_matches_reference_loop():
     for k, img in enumerate(images):
         hyb, trh = ocascade.detect_image(
             img, m["header"], m["network_types"], m["networks"], m["classifiers"], 0.2, m["num_face_stages"],
-            cut_offs_face=CUT,
-            flow_execute=lambda f, x: gpu_flow[id(f)].execute(x.astype(np.uint8), out_dtype=np.float32).astype(np.float64),
+            cut_offs_face=CUT, eye_header=m["header_eye"],
+            flow_execute=lambda f, x: gpu_flow[id(f)].execute(
+                x.astype(np.uint8) if np.array_equal(x, np.rint(x)) else x.astype(np.float32),
+                out_dtype=np.float32).astype(np.float64),
             regression=lambda c, x, lab: gpu_head[id(c)].regression(x.astype(np.float32), lab))
         hyb_counts += trh["stage_counts"]
         assert trace["raw"][k].shape == trh["raw"].shape
-        assert np.allclose(trace["raw"][k], trh["raw"], rtol=0, atol=1e-9), np.abs(trace["raw"][k] - trh["raw"]).max()
-        assert np.allclose(got[k], hyb, rtol=0, atol=1e-9)
+        # face boxes / angles / confidence: identical; eye coordinates: the contrast-normalised eye patches are
+        # rounded to float32 from a double mean / std that numpy sums pairwise and the kernel sequentially
+        assert np.allclose(trace["raw"][k][:, [0, 1, 2, 3, 4, 9]], trh["raw"][:, [0, 1, 2, 3, 4, 9]], rtol=0, atol=1e-9)
+        assert np.allclose(trace["raw"][k], trh["raw"], rtol=0, atol=1e-4), np.abs(trace["raw"][k] - trh["raw"]).max()
+        assert np.allclose(got[k], hyb, rtol=0, atol=1e-4)
 
         purged, tr = ocascade.detect_image(img, m["header"], m["network_types"], m["networks"], m["classifiers"], 0.2,
-                                           m["num_face_stages"], cut_offs_face=CUT)
+                                           m["num_face_stages"], cut_offs_face=CUT, eye_header=m["header_eye"])
         ref_counts += tr["stage_counts"]
         raw = trace["raw"][k]
         assert raw.shape == tr["raw"].shape, (k, raw.shape, tr["raw"].shape)
@@ -157,3 +163,40 @@ def test_empty_and_tiny_inputs():
     det2 = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=[-1.0] * 10)  # everything discarded at stage 0
     got2, trace2 = det2.detect([img], smallest_face=0.5, return_trace=True)
     assert got2[0].shape == (0, 10) and trace2["stage_counts"][1:].sum() == 0
+
+
+def test_contrast_normalisation_kernel():
+    import ctypes as C
+    import torch
+    from oracle import crop as ocrop
+    from pyfaceanalysis_b200 import _lib
+    rng = np.random.default_rng(3)
+    n, dim = 200, 4096
+    x = rng.integers(0, 256, (n, dim)).astype(np.float32)
+    x[5] = 77.0                                                   # constant patch: std 0 -> +1e-8 guard
+    tiles = (n + 127) // 128
+    t = np.zeros((tiles, dim, 128), dtype=np.float32)
+    for k in range(tiles):
+        blk = x[k * 128:(k + 1) * 128]
+        t[k, :, :len(blk)] = blk.T
+    d = torch.as_tensor(t, device="cuda:0")
+    _lib.check(_lib.load().hgsfa_contrast_avg_std_device(C.c_void_p(d.data_ptr()), n, dim, 0.11, 0.15, None))
+    got = d.cpu().numpy()
+    ref = ocrop.contrast_avg_std(x.astype(np.float64), 0.11, 0.15)
+    for k in range(tiles):
+        blk = ref[k * 128:(k + 1) * 128]
+        assert np.allclose(got[k, :, :len(blk)].T, blk, rtol=1e-6, atol=1e-6)
+
+
+def test_eye_stage_discards_far_eyes():
+    """|reg| >= 9 drops the face; confidences keep the reference's un-filtered indexing (FaceDetectUpdated.py:1036-1041)."""
+    from pyfaceanalysis_b200.cascade import FaceDetector
+    m = cm.cached_models()
+    nets, clfs = _gpu_models(m)
+    det = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=CUT, header_eye=m["header_eye"])
+    img = cm.test_scene(6)[0]
+    got, trace = det.detect([img], smallest_face=0.2, return_trace=True)
+    purged, tr = ocascade.detect_image(img, m["header"], m["network_types"], m["networks"], m["classifiers"], 0.2,
+                                       m["num_face_stages"], cut_offs_face=CUT, eye_header=m["header_eye"])
+    assert trace["raw"][0].shape == tr["raw"].shape
+    assert len(trace["raw"][0]) <= trace["stage_counts"][-1]
