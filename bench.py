@@ -329,7 +329,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             threads = min(12, os.cpu_count() or 1)
-            n_sample = 8192
+            n_sample = 32768
             v, secs = cpu_oracle_windows_per_s(flow, n_sample, threads)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": "%d windows x 4096 px (same distribution), float64 numpy oracle, %.1f s"

@@ -219,6 +219,7 @@ class FaceDetector(object):
         scratch = torch.empty(max(1, (n0 + 1023) // 1024), dtype=torch.int32, device=dev)
         sl = None
         n = n0
+        disc_scores = {}
         min_r = net_mins / 0.825
         max_r = net_maxs / 0.825
 
@@ -240,13 +241,9 @@ class FaceDetector(object):
                 sl = net.execute_torch(patches, layout=_lib.TILED, n=n)
             elif sl is None:
                 raise ValueError("stage %s reuses features but none were computed" % full_type)
-            D = clf.input_dim
-            if sl.shape[1] < D:
-                raise ValueError("x has dimension %d, should be %d" % (sl.shape[1], D))
-            reg = torch.empty(n, dtype=torch.float64, device=dev)
-            _lib.check(lib.hgsfa_gauss_regress_device(clf.handle, C.c_void_p(sl.data_ptr()), _lib.F32, n, sl.stride(0),
-                                                      C.c_void_p(self._labels_dev(clf).data_ptr()),
-                                                      C.c_void_p(reg.data_ptr()), None, None, None, sp))
+            reg = self._regress(clf, sl, n, sp)
+            if return_trace and ntype == "Disc":
+                disc_scores[full_type] = reg.cpu().numpy()
             params = np.array([net_Dx, net_Dy, net_Dang, rw, rh, min_r, max_r, self.cfg["tolerance_posxy_deviation"],
                                self.cfg["tolerance_scale_deviation"], self.cfg["tolerance_angle_deviation"], 0.825,
                                self.cut_offs[serial]], dtype=np.float64)
@@ -309,5 +306,5 @@ class FaceDetector(object):
         per_image_raw = [raw[im_of == k] for k in range(len(images))]
         result = [purge_detections(r) if len(r) else np.zeros((0, 10)) for r in per_image_raw]
         if return_trace:
-            return result, dict(stage_counts=counts, raw=per_image_raw, n_windows=n0)
+            return result, dict(stage_counts=counts, raw=per_image_raw, n_windows=n0, disc_scores=disc_scores)
         return result
