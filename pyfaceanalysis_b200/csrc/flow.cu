@@ -325,7 +325,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       dp.TW = (int)ph[5]; dp.dst = (int)ph[6]; dp.row0 = (int)ph[7]; dp.w_off = (int)ph[8]; dp.b_off = (int)ph[9];
       dp.term_off = (int)ph[10]; dp.n_seg = (int)ph[11]; dp.SW = (int)ph[14];
       const bool psane =
-          dp.K > 0 && (dp.NT == 8 || dp.NT == 16 || dp.NT == 24 || dp.NT == 32) && dp.NTL >= 1 && dp.KS >= 1 &&
+          dp.K > 0 && dp.NT >= 8 && dp.NT <= 32 && dp.NT % 4 == 0 && dp.NTL >= 1 && dp.KS >= 1 &&
           dp.TW >= 1 && dp.NTL * dp.KS * dp.TW == d.warps && dp.Npad == dp.NT * dp.NTL && (dp.SW == 1 || dp.SW == 2) &&
           (dp.SW == 1 || dp.NT <= 16) && d.twc % dp.SW == 0 &&
           (dp.KS & (dp.KS - 1)) == 0 && (dp.dst & (DST_GLOBAL | DST_ROWS)) && dp.row0 >= 0 &&

@@ -596,15 +596,23 @@ __global__ void __launch_bounds__(THREADS, (NTMAX <= 16 ? 2 : 1))
     for (int p = 0; p < op.n_passes; ++p) {
       const PassDev& ps = op.pass[p];
       const int code = ps.NT * 4 + ps.SW;
+#define HG_PASS(NT_, SW_) run_pass<IN_T, NT_, SW_>(op, ps, node, tile0, ntiles, stage, smem, xout)
       switch (code) {
-        case 8 * 4 + 1: run_pass<IN_T, 8, 1>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
-        case 16 * 4 + 1: run_pass<IN_T, 16, 1>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
-        case 8 * 4 + 2: run_pass<IN_T, 8, 2>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
-        case 16 * 4 + 2: if constexpr (NTMAX >= 32) run_pass<IN_T, 16, 2>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
-        case 24 * 4 + 1: if constexpr (NTMAX >= 32) run_pass<IN_T, 24, 1>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
-        case 32 * 4 + 1: if constexpr (NTMAX >= 32) run_pass<IN_T, 32, 1>(op, ps, node, tile0, ntiles, stage, smem, xout); break;
+        // <= 64 accumulator registers per thread
+        case 8 * 4 + 1: HG_PASS(8, 1); break;
+        case 12 * 4 + 1: HG_PASS(12, 1); break;
+        case 16 * 4 + 1: HG_PASS(16, 1); break;
+        case 8 * 4 + 2: HG_PASS(8, 2); break;
+        // up to 128 accumulator registers per thread
+        case 12 * 4 + 2: if constexpr (NTMAX >= 32) HG_PASS(12, 2); break;
+        case 16 * 4 + 2: if constexpr (NTMAX >= 32) HG_PASS(16, 2); break;
+        case 20 * 4 + 1: if constexpr (NTMAX >= 32) HG_PASS(20, 1); break;
+        case 24 * 4 + 1: if constexpr (NTMAX >= 32) HG_PASS(24, 1); break;
+        case 28 * 4 + 1: if constexpr (NTMAX >= 32) HG_PASS(28, 1); break;
+        case 32 * 4 + 1: if constexpr (NTMAX >= 32) HG_PASS(32, 1); break;
         default: break;
       }
+#undef HG_PASS
       if (!op.simple) __syncthreads();   // shared rows of this pass visible; stage consumed after the last pass
     }
     // ---- hand the stage back.  Simple ops (one pass, no K-split) have no CTA-wide barrier at all: warps

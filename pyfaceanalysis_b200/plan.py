@@ -383,6 +383,7 @@ class OpSpec(object):
         self.clip = (-np.inf, np.inf)   # saturation applied when results are stored to the output buffer
 
 
+NT_CHOICES = tuple(int(v) for v in __import__("os").environ.get("HGSFA_NT_CHOICES", "8,12,16,20,24,28,32").split(","))
 WIDE_TILES = __import__("os").environ.get("HGSFA_WIDE_TILES", "0") != "0"   # measured: no gain on U11L_64 (profiles/README_r01.md)
 
 
@@ -394,7 +395,7 @@ def _choose_tile(n_real):
     operand conversion over more FMAs."""
     best = None
     for ntl in (1, 2, 4):
-        for nt in (8, 16, 24, 32):
+        for nt in NT_CHOICES:
             if nt * ntl < n_real:
                 continue
             key = (nt * ntl, ntl) if WIDE_TILES else (nt * ntl, nt > 16, -nt)
@@ -558,7 +559,7 @@ def _decompose(op):
         ps["w_off"] = off
         off += ps["K"] * ps["Npad"]
     op.param_floats = -(-off // 4) * 4
-    wide = any(ps["NT"] > 16 or (ps["NT"] == 16 and TWO_SLOTS) for ps in op.passes)
+    wide = any(ps["NT"] > 16 or (ps["NT"] > 8 and TWO_SLOTS) for ps in op.passes)
 
     def best_twc(warps, budget):
         # enough slots that no pass needs a K-split, then as many as shared memory allows
@@ -581,9 +582,12 @@ def _decompose(op):
             choice = (4, t)
     if choice is None:
         t = best_twc(8, SMEM_LIMIT if wide else SMEM_TARGET) or best_twc(8, SMEM_LIMIT)
-        if t is None:
+        if t is not None:
+            choice = (8, t)
+        elif all(ps["NTL"] <= 4 for ps in op.passes) and best_twc(4, SMEM_LIMIT) is not None:
+            choice = (4, best_twc(4, SMEM_LIMIT))       # one 4-warp CTA per SM: smaller K-split scratch
+        else:
             raise UnsupportedFlow("a receptive field of %d inputs does not fit in shared memory" % op.d_in)
-        choice = (8, t)
     op.warps, op.twc = choice
     for ps in op.passes:
         ps["SW"], ps["TW"], ps["KS"] = _pass_split(ps, op.twc, op.warps)
@@ -618,7 +622,7 @@ def _fuse_id_pow(segs):
     return out
 
 
-FOLD_BIAS = float(_os.environ.get("HGSFA_FOLD_BIAS", "1.7"))
+FOLD_BIAS = float(_os.environ.get("HGSFA_FOLD_BIAS", "1.5"))
 FUSE_ID_POW = _os.environ.get("HGSFA_FUSE_ID_POW", "1") != "0"
 
 

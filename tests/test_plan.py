@@ -158,9 +158,14 @@ def test_expansion_tables_match_oracle_functions():
 
 
 def test_tile_choice_and_segments():
-    assert plan._choose_tile(13) == (16, 1) and plan._choose_tile(20) == (24, 1)
-    assert plan._choose_tile(27)[0] * plan._choose_tile(27)[1] == 32
-    assert plan._choose_tile(48) == (24, 2) and plan._choose_tile(60) == (16, 4)
+    assert plan._choose_tile(13) == (16, 1) and plan._choose_tile(20) == (20, 1)
+    assert plan._choose_tile(12) == (12, 1) and plan._choose_tile(27) == (28, 1)
+    for n in range(1, 129):         # column tiles come in multiples of 4: never more than 3 padded columns up to 32
+        nt, ntl = plan._choose_tile(n)
+        assert nt % 4 == 0 and 8 <= nt <= 32 and ntl in (1, 2, 4) and nt * ntl >= n
+        if 8 <= n <= 32:
+            assert nt * ntl - n < 4
+    assert plan._choose_tile(60)[0] * plan._choose_tile(60)[1] == 64
     with pytest.raises(plan.UnsupportedFlow):
         plan._choose_tile(300)
     t = ex.lower(["identity", "unsigned_08expo", "s3QT"], 6)
