@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "layer.cuh"
+#include "layer_tc.cuh"
 
 namespace hgsfa {
 
@@ -128,7 +129,42 @@ struct OpHost {
   int scratch_floats;    // K-split scratch (floats)
   size_t smem_bytes[2];  // dynamic shared memory for [f32 input, u8 input]
   int nstages[2];
+  bool tc;               // runs on the tensor cores (layer_tc.cuh) instead of the FFMA kernel
+  TcOpDev tcd;
+  size_t tc_smem[2];
 };
+
+// shared-memory layout of layer_tc_kernel for input element size `el`; returns total bytes
+static size_t layout_tc(TcOpDev& d, int n_segs, int el) {
+  auto up = [](size_t x) { return (x + 127) & ~size_t(127); };
+  size_t off = TCB_BYTES;
+  d.sm_terms = (int)off;
+  off += up(size_t(d.n_terms) * sizeof(Term16));
+  d.sm_toff = (int)off;
+  off += up(size_t(d.n_terms) * 8);
+  d.sm_segs = (int)off;
+  off += up(size_t(n_segs) * sizeof(Seg));
+  d.sm_chunkseg = (int)off;
+  off += up(size_t(d.n_chunks + 1) * 4);
+  d.sm_bias = (int)off;
+  off += up(size_t(2) * d.Npad16 * 4);
+  d.sm_raw_bytes = int(size_t(d.d_in) * TILE * el);
+  d.sm_xstage_bytes = (int)up(size_t(d.twc) * d.sm_raw_bytes + size_t(d.head_floats) * 4);
+  d.sm_x0 = (int)off;
+  off += size_t(d.nstx) * d.sm_xstage_bytes;
+  d.sm_wstage_bytes = (int)up(size_t(d.wchunk_floats) * 4);
+  d.sm_w0 = (int)off;
+  off += size_t(d.nw) * d.sm_wstage_bytes;
+  return off;
+}
+
+static inline float tf32_rn(float x) {   // round to nearest TF32 (10 mantissa bits), ties away from zero
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xffffe000u;
+  std::memcpy(&x, &u, 4);
+  return x;
+}
 
 // shared-memory layout for input element size `el`; returns total bytes (0 if nothing fits)
 static size_t layout_op(OpDev& d, int scratch_floats, int el, int* nstages_out) {
@@ -171,6 +207,7 @@ struct hgsfa_plan_s {
   std::vector<OpHost> ops;
   DevBuf params;                     // the whole blob: every plan array is an offset into it
   DevBuf tin, front[2], mid, back[2], stage_x[2], stage_y[2];
+  std::vector<DevBuf> tc_bufs;       // tensor-core operand images (weights split into TF32 hi / lo, chunked)
   // measured on B200 (profiles/README_r01.md): launches of >= 128 Ki windows hide the wave tail of the
   // one-CTA-per-SM layer kernels; smaller chunks only pay when the batch itself is small
   int64_t front_chunk = 131072, back_chunk = 262144;
@@ -179,6 +216,7 @@ struct hgsfa_plan_s {
   double last_ms = 0.0;
   int sm_count = 148;
   int max_npc = 16;
+  int max_npc_tc = 32;
 };
 
 namespace {
@@ -226,6 +264,28 @@ int launch_layer(hgsfa_plan_s* pl, OpHost& op, const void* xin, float* xout, int
   return 0;
 }
 
+template <typename IN_T>
+int launch_layer_tc(hgsfa_plan_s* pl, OpHost& op, const void* xin, float* xout, int64_t ntiles, cudaStream_t st) {
+  if (ntiles <= 0) return 0;
+  const int v = sizeof(IN_T) == 1 ? 1 : 0;
+  TcOpDev d = op.tcd;
+  {
+    const int64_t groups = ceil_div(ntiles, d.twc);
+    int64_t npc = (groups * d.n_nodes) / (int64_t(pl->sm_count) * 6);
+    if (npc < 1) npc = 1;
+    if (npc > pl->max_npc_tc) npc = pl->max_npc_tc;
+    if (npc > d.n_nodes) npc = d.n_nodes;
+    d.npc = (int)npc;
+  }
+  const size_t smem = layout_tc(d, d.n_segs, (int)sizeof(IN_T));
+  HG_CHECK(smem <= op.tc_smem[v], "tensor-core layer launch needs %zu bytes of shared memory, reserved %zu", smem, op.tc_smem[v]);
+  dim3 grid((unsigned)ceil_div(ntiles, d.twc), (unsigned)ceil_div(d.n_nodes, d.npc));
+  layer_tc_kernel<IN_T><<<grid, TC_THREADS, smem, st>>>(d, static_cast<const IN_T*>(xin), xout, ntiles);
+  pl->launches++;
+  HG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int plan_fail(hgsfa_plan_s* pl, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -233,6 +293,7 @@ int plan_fail(hgsfa_plan_s* pl, const char* fmt, ...) {
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
   pl->params.release();
+  for (auto& b : pl->tc_bufs) b.release();
   delete pl;
   return fail("hgsfa_plan_create: %s", buf);
 }
@@ -274,6 +335,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
     OpDev& d = op.dev;
     d.n_nodes = (int)oh[0]; d.d_in = (int)oh[1]; d.in_dim = (int)oh[2]; d.out_dim = (int)oh[3];
     d.n_passes = (int)oh[4]; d.shared = (int)(oh[5] & 0xff); d.warps = (int)((oh[5] >> 8) & 0xff); d.n_rows = (int)oh[6];
+    op.tc = ((oh[5] >> 16) & 0xff) == 1;
     d.twc = (int)oh[7];
     op.alg_flops = oh[8]; op.exe_flops = oh[9];
     d.npc = (int)oh[10]; d.n_runs = (int)oh[11];
@@ -285,7 +347,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
     d.param_floats = (int)oh[14]; d.n_terms = (int)oh[15];
     const bool sane = d.n_nodes > 0 && d.n_nodes <= 65535 * 64 && d.d_in > 0 && d.d_in < 32768 && d.in_dim == cur_dim &&
                       d.out_dim > 0 && d.n_passes >= 1 && d.n_passes <= MAX_PASSES &&
-                      (d.twc == 1 || d.twc == 2 || d.twc == 4 || d.twc == 8 || d.twc == 16) && d.n_rows >= 0 && d.npc >= 1 &&
+                      (op.tc ? (d.twc >= 1 && d.twc <= TC_MAX_TW) : (d.twc == 1 || d.twc == 2 || d.twc == 4 || d.twc == 8 || d.twc == 16)) && d.n_rows >= 0 && d.npc >= 1 &&
                       (d.warps == 4 || d.warps == 8) && d.n_runs >= 1 && d.n_runs <= d.d_in && d.param_floats > 0 && d.param_floats % 4 == 0 &&
                       d.n_terms > 0;
     if (!sane)
@@ -324,11 +386,13 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       dp.K = (int)ph[0]; dp.Npad = (int)ph[1]; dp.NT = (int)ph[2]; dp.NTL = (int)ph[3]; dp.KS = (int)ph[4];
       dp.TW = (int)ph[5]; dp.dst = (int)ph[6]; dp.row0 = (int)ph[7]; dp.w_off = (int)ph[8]; dp.b_off = (int)ph[9];
       dp.term_off = (int)ph[10]; dp.n_seg = (int)ph[11]; dp.SW = (int)ph[14];
+      const bool tiles_ok =
+          op.tc ? (d.n_passes == 1 && d.n_rows == 0 && dp.dst == DST_GLOBAL && dp.Npad >= 1 && dp.Npad % 4 == 0)
+                : (dp.NT >= 8 && dp.NT <= 32 && dp.NT % 4 == 0 && dp.NTL >= 1 && dp.KS >= 1 && dp.TW >= 1 &&
+                   dp.NTL * dp.KS * dp.TW == d.warps && dp.Npad == dp.NT * dp.NTL && (dp.SW == 1 || dp.SW == 2) &&
+                   (dp.SW == 1 || dp.NT <= 16) && d.twc % dp.SW == 0 && (dp.KS & (dp.KS - 1)) == 0);
       const bool psane =
-          dp.K > 0 && dp.NT >= 8 && dp.NT <= 32 && dp.NT % 4 == 0 && dp.NTL >= 1 && dp.KS >= 1 &&
-          dp.TW >= 1 && dp.NTL * dp.KS * dp.TW == d.warps && dp.Npad == dp.NT * dp.NTL && (dp.SW == 1 || dp.SW == 2) &&
-          (dp.SW == 1 || dp.NT <= 16) && d.twc % dp.SW == 0 &&
-          (dp.KS & (dp.KS - 1)) == 0 && (dp.dst & (DST_GLOBAL | DST_ROWS)) && dp.row0 >= 0 &&
+          dp.K > 0 && tiles_ok && (dp.dst & (DST_GLOBAL | DST_ROWS)) && dp.row0 >= 0 &&
           (!(dp.dst & DST_ROWS) || dp.row0 + dp.Npad <= d.n_rows) && dp.w_off >= 0 && dp.w_off % 4 == 0 && dp.b_off >= 0 &&
           dp.w_off + dp.K * dp.Npad <= d.param_floats && dp.b_off + dp.Npad <= d.param_floats && dp.term_off >= 0 &&
           dp.term_off + dp.K <= d.n_terms && dp.n_seg >= 1;
@@ -359,8 +423,131 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       dp.segs = reinterpret_cast<const Seg*>(dev_ptr(segs));
       dp.n_valid = reinterpret_cast<const int*>(dev_ptr(n_valid));
       dp.col_off = reinterpret_cast<const int*>(dev_ptr(col_off));
-      if (dp.NT * dp.SW > 16) op.wide = true;
-      if (dp.KS > 1) op.scratch_floats = std::max(op.scratch_floats, (d.warps / 2) * dp.SW * dp.NT * TILE);
+      if (!op.tc && dp.NT * dp.SW > 16) op.wide = true;
+      if (!op.tc && dp.KS > 1) op.scratch_floats = std::max(op.scratch_floats, (d.warps / 2) * dp.SW * dp.NT * TILE);
+      if (op.tc) {
+        // ---- tensor-core operand images (layer_tc.cuh): ph[2..5] = accumulator sets, receptive-field stages,
+        // weight-ring stages, A stages chosen by the plan compiler; everything else is derived here
+        TcOpDev& t = op.tcd;
+        t = TcOpDev{};
+        t.n_nodes = d.n_nodes; t.d_in = d.d_in; t.in_dim = d.in_dim; t.out_dim = d.out_dim; t.shared = d.shared;
+        t.twc = d.twc; t.npc = 1; t.n_runs = d.n_runs; t.clip_lo = d.clip_lo; t.clip_hi = d.clip_hi;
+        t.nd = (int)ph[2]; t.nstx = (int)ph[3]; t.nw = (int)ph[4]; t.na = (int)ph[5];
+        int n_max = 1;
+        for (int nd = 0; nd < d.n_nodes; ++nd) n_max = std::max(n_max, (int)n_valid[nd]);
+        t.K = dp.K; t.Npad16 = (n_max + 15) & ~15;
+        t.n_terms = d.n_terms;
+        const int d_pad = (d.d_in + 3) & ~3;
+        t.head_floats = (d_pad + t.Npad16 + 2 * d.n_terms + 3) & ~3;
+        t.wchunk_floats = 2 * TC_CK * t.Npad16;
+        const int cols = t.nd * t.twc * t.Npad16 + t.na * 2 * TC_CK;
+        t.tmem_cols = 32;
+        while (t.tmem_cols < cols) t.tmem_cols *= 2;
+        if (!(t.nd == 1 || t.nd == 2) || !(t.nstx == 1 || t.nstx == 2) || t.nw < 2 || t.nw > 4 || !(t.na == 2 || t.na == 4) ||
+            t.twc > TC_MAX_TW || t.Npad16 > 128 || cols > 512 || n_max > dp.Npad)
+          return plan_fail(pl, "op %lld: bad tensor-core configuration (twc=%d Npad16=%d nd=%d nstx=%d nw=%d na=%d cols=%d)",
+                           (long long)o, t.twc, t.Npad16, t.nd, t.nstx, t.nw, t.na, cols);
+        // segments: identity+power fusions undone; every segment starts at a multiple of 8 A columns and is
+        // padded to a multiple of 8 (zero weight rows), then split at chunk boundaries.  For the kernel a
+        // piece is (op, k0, k1 = A columns, p, kind = real terms, ibase, nomean, pad1 = first term-table entry).
+        std::vector<Seg> tsegs;
+        std::vector<int> knew(dp.K, 0);          // term k -> A column
+        int cursor = 0;
+        auto push = [&](Seg sgm) {               // sgm.k0 / k1: ORIGINAL term range
+          int real = sgm.k1 - sgm.k0, tk = sgm.k0, ib = sgm.ibase;
+          for (int k = sgm.k0; k < sgm.k1; ++k) knew[k] = cursor + (k - sgm.k0);
+          int pos = cursor;
+          const int end = cursor + ((real + 7) & ~7);
+          while (pos < end) {
+            Seg piece = sgm;
+            piece.k0 = pos;
+            piece.k1 = std::min(end, (pos / TC_CK + 1) * TC_CK);
+            const int len = piece.k1 - piece.k0;
+            piece.kind = std::min(real, len);
+            piece.ibase = ib;
+            piece.pad1 = tk;
+            tsegs.push_back(piece);
+            if (ib >= 0) ib += len;
+            tk += piece.kind;
+            real -= piece.kind;
+            pos = piece.k1;
+          }
+          cursor = end;
+        };
+        for (int sgi = 0; sgi < dp.n_seg; ++sgi) {
+          Seg sgm = segs[sgi];
+          if (sgm.kind != 0) return plan_fail(pl, "op %lld: tensor-core ops take receptive-field operands only", (long long)o);
+          if (sgm.op == OP_ID_POW) {
+            const int half = (sgm.k1 - sgm.k0) / 2;
+            Seg a = sgm, b = sgm;
+            a.op = OP_ID; a.k1 = sgm.k0 + half;
+            b.op = OP_ABSPOW; b.k0 = sgm.k0 + half; b.nomean = 0;
+            push(a); push(b);
+          } else {
+            push(sgm);
+          }
+        }
+        t.Kpad = cursor;
+        t.n_chunks = (t.Kpad + TC_CK - 1) / TC_CK;
+        std::vector<int32_t> chunk_seg(t.n_chunks + 1, 0);
+        {
+          size_t sgi = 0;
+          for (int c = 0; c < t.n_chunks; ++c) {
+            chunk_seg[c] = (int32_t)sgi;
+            while (sgi < tsegs.size() && tsegs[sgi].k0 < (c + 1) * TC_CK) ++sgi;
+          }
+          chunk_seg[t.n_chunks] = (int32_t)tsegs.size();
+        }
+        t.n_segs = (int)tsegs.size();
+        // head = x_mean | bias;  weight chunks = TF32 hi image | lo image, canonical K-major core matrices
+        const size_t head_bytes = size_t(n_w) * t.head_floats * 4;
+        const size_t wimg_bytes = size_t(n_w) * t.n_chunks * t.wchunk_floats * 4;
+        const size_t seg_bytes = (tsegs.size() * sizeof(Seg) + 15) & ~size_t(15);
+        const size_t cs_bytes = (chunk_seg.size() * 4 + 15) & ~size_t(15);
+        std::vector<uint8_t> host(head_bytes + wimg_bytes + seg_bytes + cs_bytes, 0);
+        float* head = reinterpret_cast<float*>(host.data());
+        float* wimg = reinterpret_cast<float*>(host.data() + head_bytes);
+        const int nb8 = t.Npad16 / 8;
+        for (int w = 0; w < n_w; ++w) {
+          const float* pw = params + size_t(w) * d.param_floats;
+          for (int i = 0; i < d.d_in; ++i) head[size_t(w) * t.head_floats + i] = pw[i];
+          for (int n = 0; n < std::min(dp.Npad, t.Npad16); ++n) head[size_t(w) * t.head_floats + d_pad + n] = pw[dp.b_off + n];
+          for (int k = 0; k < d.n_terms; ++k) {     // operand means of the product terms, in term-table order
+            head[size_t(w) * t.head_floats + d_pad + t.Npad16 + 2 * k] = pw[terms[k].i];
+            head[size_t(w) * t.head_floats + d_pad + t.Npad16 + 2 * k + 1] = pw[terms[k].j];
+          }
+          for (int k = 0; k < dp.K; ++k) {
+            const int c = knew[k] / TC_CK, kk = knew[k] % TC_CK;
+            float* img = wimg + (size_t(w) * t.n_chunks + c) * t.wchunk_floats;
+            for (int n = 0; n < std::min(dp.Npad, t.Npad16); ++n) {
+              const float wv = pw[dp.w_off + size_t(k) * dp.Npad + n];
+              const float hi = tf32_rn(wv);
+              const size_t off = (size_t((kk >> 2) * nb8 + (n >> 3)) * 8 + (n & 7)) * 4 + (kk & 3);
+              img[off] = hi;
+              img[size_t(TC_CK) * t.Npad16 + off] = tf32_rn(wv - hi);
+            }
+          }
+        }
+        std::memcpy(host.data() + head_bytes + wimg_bytes, tsegs.data(), tsegs.size() * sizeof(Seg));
+        std::memcpy(host.data() + head_bytes + wimg_bytes + seg_bytes, chunk_seg.data(), chunk_seg.size() * 4);
+        pl->tc_bufs.emplace_back();
+        DevBuf& buf = pl->tc_bufs.back();
+        if (buf.reserve(host.size())) return plan_fail(pl, "out of device memory for tensor-core operands");
+        if (cudaMemcpy(buf.p, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+          return plan_fail(pl, "tensor-core operand upload failed");
+        const uint8_t* tb = static_cast<const uint8_t*>(buf.p);
+        t.head = reinterpret_cast<const float*>(tb);
+        t.wimg = reinterpret_cast<const float*>(tb + head_bytes);
+        t.segs = reinterpret_cast<const Seg*>(tb + head_bytes + wimg_bytes);
+        t.chunk_seg = reinterpret_cast<const int*>(tb + head_bytes + wimg_bytes + seg_bytes);
+        t.runs = d.runs; t.out_col = d.out_col; t.n_valid = dp.n_valid; t.col_off = dp.col_off; t.terms = d.terms;
+        for (int v = 0; v < 2; ++v) {
+          TcOpDev tmp = t;
+          op.tc_smem[v] = layout_tc(tmp, t.n_segs, v ? 1 : 4);
+        }
+        if (op.tc_smem[0] > size_t(227) * 1024)
+          return plan_fail(pl, "op %lld: tensor-core layout needs %zu bytes of shared memory", (long long)o, op.tc_smem[0]);
+      }
     }
     if (!cur.ok) break;
     // barrier-free hand-over of stages for one-pass, no-K-split ops: measured equal to the per-node barrier on
@@ -371,6 +558,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
       tmp.npc = 64;   // worst case for the reservation: as many stages as ever fit
       op.smem_bytes[v] = layout_op(tmp, op.scratch_floats, v ? 1 : 4, &op.nstages[v]);
     }
+    if (op.tc) { op.smem_bytes[0] = op.smem_bytes[1] = 1; }
     if (op.smem_bytes[0] == 0)
       return plan_fail(pl, "op %lld does not fit in 227 KB of shared memory (d_in=%d twc=%d)", (long long)o, d.d_in, d.twc);
     cur_dim = d.out_dim;
@@ -379,8 +567,15 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
   if (!cur.ok || (int64_t)pl->ops.size() != n_ops || cur_dim != pl->output_dim)
     return plan_fail(pl, "truncated or inconsistent blob (%zu of %lld ops parsed, final dim %lld vs %lld)", pl->ops.size(),
                      (long long)n_ops, (long long)cur_dim, (long long)hdr[1]);
-  size_t max_smem = 0;
-  for (auto& op : pl->ops) max_smem = std::max(max_smem, std::max(op.smem_bytes[0], op.smem_bytes[1]));
+  size_t max_smem = 0, max_tc = 0;
+  for (auto& op : pl->ops) {
+    if (op.tc) max_tc = std::max(max_tc, std::max(op.tc_smem[0], op.tc_smem[1]));
+    else max_smem = std::max(max_smem, std::max(op.smem_bytes[0], op.smem_bytes[1]));
+  }
+  if (max_tc > 0 &&
+      (cudaFuncSetAttribute(layer_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess ||
+       cudaFuncSetAttribute(layer_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess))
+    return plan_fail(pl, "cannot reserve %zu bytes of dynamic shared memory for the tensor-core kernel", max_tc);
   cudaError_t es[4] = {
       cudaFuncSetAttribute(layer_kernel<uint8_t, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
       cudaFuncSetAttribute(layer_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
@@ -417,6 +612,7 @@ extern "C" int hgsfa_plan_destroy(hgsfa_plan_t pl) {
   if (pl->stream) cudaStreamSynchronize(pl->stream);
   if (pl->copy_stream) cudaStreamSynchronize(pl->copy_stream);
   pl->params.release(); pl->tin.release(); pl->mid.release();
+  for (auto& b : pl->tc_bufs) b.release();
   for (int i = 0; i < 2; ++i) {
     pl->front[i].release(); pl->back[i].release(); pl->stage_x[i].release(); pl->stage_y[i].release();
     if (pl->ev_h2d[i]) cudaEventDestroy(pl->ev_h2d[i]);
@@ -506,7 +702,8 @@ int run_ops(hgsfa_plan_s* pl, int o0, int o1, const void* xin, bool xin_u8, floa
   for (int o = o0; o < o1; ++o) {
     OpHost& op = pl->ops[o];
     float* dst = (o == o1 - 1) ? final_out : static_cast<float*>(pp[(o - o0) & 1].p);
-    int rc = cur_u8 ? launch_layer<uint8_t>(pl, op, cur, dst, ntiles, st) : launch_layer<float>(pl, op, cur, dst, ntiles, st);
+    int rc = op.tc ? (cur_u8 ? launch_layer_tc<uint8_t>(pl, op, cur, dst, ntiles, st) : launch_layer_tc<float>(pl, op, cur, dst, ntiles, st))
+                   : (cur_u8 ? launch_layer<uint8_t>(pl, op, cur, dst, ntiles, st) : launch_layer<float>(pl, op, cur, dst, ntiles, st));
     if (rc) return rc;
     cur = dst;
     cur_u8 = false;

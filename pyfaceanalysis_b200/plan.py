@@ -380,6 +380,8 @@ class OpSpec(object):
         self.alg_flops = 0
         self.exe_flops = 0
         self.mode = ""
+        self.engine = "ffma"    # "tc": tensor-core kernel (csrc/layer_tc.cuh)
+        self.tc = None          # dict(nd, nstx, nw, na, Npad16, Kpad, n_chunks, tmem_cols, smem)
         self.clip = (-np.inf, np.inf)   # saturation applied when results are stored to the output buffer
 
 
@@ -411,7 +413,22 @@ def _padded_cols(n_real):
     return nt * ntl
 
 
+class _NotTensorCore(Exception):
+    pass
+
+
 def _assemble_layer(children, gather_cols, in_dim, igsfa_mode="auto"):
+    """Tensor-core engine first (one folded contraction per node: tcgen05 does not care about the extra
+    columns) when the op qualifies, else the FFMA engine with its own fold / two-pass choice."""
+    if ENGINE in ("tc", "auto") and igsfa_mode in ("auto", "fold"):
+        try:
+            return _assemble_layer_impl(children, gather_cols, in_dim, "fold", "tc")
+        except (_NotTensorCore, UnsupportedFlow):
+            pass
+    return _assemble_layer_impl(children, gather_cols, in_dim, igsfa_mode, "ffma")
+
+
+def _assemble_layer_impl(children, gather_cols, in_dim, igsfa_mode, engine):
     """children: list of node sequences (one per receptive field); gather_cols: list of index arrays."""
     n_nodes = len(children)
     d_in = len(gather_cols[0])
@@ -495,7 +512,12 @@ def _assemble_layer(children, gather_cols, in_dim, igsfa_mode="auto"):
                               col_off=col_off, K_real=K, N_real=n_real, K=K, Npad=npad))
         op.exe_flops += n_nodes * 2 * K * npad
     op.n_rows = row_cursor
-    _decompose(op)
+    if engine == "tc":
+        if not _tc_eligible(op) or (ENGINE == "auto" and op.passes[0]["K"] < TC_MIN_K):
+            raise _NotTensorCore()
+        _decompose_tc(op)
+    else:
+        _decompose(op)
     return op
 
 
@@ -598,6 +620,127 @@ def _decompose(op):
     for nd, rl in enumerate(runs):
         for r, (i0, f0, ln) in enumerate(rl):
             op.runs[nd, r] = (i0, f0, ln, 0)
+
+
+# "auto": ops with at least TC_MIN_K expansion terms per node run on the tensor cores (tcgen05, 3xTF32), smaller
+# ones on the FFMA kernel (measured cross-over, profiles/README_r01.md); "tc" / "ffma" force one engine
+ENGINE = _os.environ.get("HGSFA_ENGINE", "auto")
+TC_MIN_K = int(_os.environ.get("HGSFA_TC_MIN_K", "64"))
+TC_CK = 32          # terms per chunk (csrc/layer_tc.cuh)
+# two CTAs per SM (256 tensor-memory columns, 113 KB each): measured 56.8 vs 87.8 ms per 1M windows against one big CTA
+TC_MAX_COLS = int(_os.environ.get("HGSFA_TC_MAXCOLS", "256"))
+TC_MAX_SMEM = int(_os.environ.get("HGSFA_TC_MAXSMEM", "113")) * 1024
+
+
+def _tc_eligible(op):
+    if op.mode == "copy" or len(op.passes) != 1 or op.n_rows != 0:
+        return False
+    ps = op.passes[0]
+    if ps["dst"] != DST_GLOBAL or int(ps["n_valid"].max()) > 128:
+        return False
+    return all(sg[4] == 0 for sg in _segments(ps["terms"], op.d_in))
+
+
+def _tc_segments(segs, K):
+    """Segments as the tensor-core kernel walks them (mirrors hgsfa_plan_create): identity/power fusions
+    undone, every segment padded to a multiple of 8 A columns, split at chunk boundaries.
+    Returns (pieces, Kpad)."""
+    out = []
+    cursor = 0
+
+    def push(o, n):
+        nonlocal cursor
+        pos, end = cursor, cursor + -(-n // 8) * 8
+        while pos < end:
+            nxt = min(end, (pos // TC_CK + 1) * TC_CK)
+            out.append((o, pos, nxt))
+            pos = nxt
+        cursor = end
+    for sg in segs:
+        o, k0, k1 = sg[0], sg[1], sg[2]
+        if o == OP_ID_POW:
+            half = (k1 - k0) // 2
+            push(ex.OP_ID, half)
+            push(ex.OP_ABSPOW, half)
+        else:
+            push(o, k1 - k0)
+    return out, cursor
+
+
+def _decompose_tc(op):
+    """Tensor-core configuration of a single-pass op: tiles per CTA, accumulator sets, receptive-field stages,
+    weight-ring stages and A stages under the 512-column tensor-memory and 227 KB shared-memory budgets.
+    The score is a rough time model (MMA issue rate measured by tools/tc_probe.cu, L2 traffic of the
+    streamed weight chunks, exposed loads when a resource is single-buffered)."""
+    ps = op.passes[0]
+    K = ps["K"]
+    n_max = max(1, int(ps["n_valid"].max()))
+    npad16 = -(-n_max // 16) * 16
+    segs, kpad = _tc_segments(_fuse_id_pow(_segments(ps["terms"], op.d_in)), K)
+    n_chunks = -(-kpad // TC_CK)
+    d_pad = -(-op.d_in // 4) * 4
+    head = -(-(d_pad + npad16 + 2 * K) // 4) * 4
+    wstage = 2 * TC_CK * npad16 * 4
+
+    def up(x):
+        return (x + 127) // 128 * 128
+    fixed = 512 + 2 * up(K * 8) + up(len(segs) * 32) + up((n_chunks + 1) * 4) + up(2 * npad16 * 4)
+    t_mma = 3.0 * (kpad / 8.0) * (17.0 + 0.2 * npad16)          # ns per (node, tile)
+    best = None
+    forced = {k: int(_os.environ[e]) for k, e in (("twc", "HGSFA_TC_TWC"), ("nd", "HGSFA_TC_ND"), ("nstx", "HGSFA_TC_NSTX"),
+                                                  ("na", "HGSFA_TC_NA"), ("nw", "HGSFA_TC_NW")) if e in _os.environ}
+    for max_cols, max_smem in ((TC_MAX_COLS, TC_MAX_SMEM), (512, SMEM_LIMIT)):
+      if best is not None:
+        break
+      for twc in range(1, 9):
+        for nd in (1, 2):
+            for na in (2, 4):
+                cols = nd * twc * npad16 + na * 2 * TC_CK
+                if cols > 512:
+                    continue
+                for nstx in (1, 2):
+                    for nw in (2, 3, 4):
+                        cfg = dict(twc=twc, nd=nd, nstx=nstx, na=na, nw=nw)
+                        if any(cfg[k] != v for k, v in forced.items()):
+                            continue
+                        smem = fixed + nstx * up(twc * op.d_in * TILE * 4 + head * 4) + nw * up(wstage)
+                        if smem > SMEM_LIMIT or cols > max_cols or smem > max_smem:
+                            continue
+                        t_w = n_chunks * wstage / twc / 10.0                          # L2 -> SM bytes at ~10 B/ns per SM
+                        t = max(t_mma, t_w)
+                        if nstx == 1:
+                            t += (1500.0 + op.d_in * TILE * 4 * twc / 100.0) / twc    # exposed receptive-field load per node
+                        if nd == 1:
+                            t += 500.0 / twc                                          # MMA pipe drained before the epilogue
+                        t += 300.0 / twc                                              # per-node hand-overs
+                        t += (0.0 if na == 4 else 0.05 * t_mma) + (0.0 if nw >= 3 else 0.03 * t_mma)
+                        key = (t, smem)
+                        if best is None or key < best[0]:
+                            best = (key, cfg, cols, smem)
+    if best is None:
+        raise UnsupportedFlow("a receptive field of %d inputs does not fit in shared memory" % op.d_in)
+    _, cfg, cols, smem = best
+    tmem = 32
+    while tmem < cols:
+        tmem *= 2
+    op.engine = "tc"
+    op.warps, op.twc = 4, cfg["twc"]
+    op.tc = dict(cfg, Npad16=npad16, Kpad=kpad, n_chunks=n_chunks, tmem_cols=tmem, smem=smem, n_segs=len(segs))
+    ps["SW"], ps["TW"], ps["KS"] = 1, 1, 1
+    off = d_pad
+    ps["b_off"] = off
+    off += ps["Npad"]
+    ps["w_off"] = off
+    off += ps["K"] * ps["Npad"]
+    op.param_floats = -(-off // 4) * 4
+    op.exe_flops = op.n_nodes * 3 * 2 * kpad * npad16          # tensor-pipe flops of the 3xTF32 split
+    op.npc = max(1, min(8, op.n_nodes // 32))
+    runs = [_gather_runs(g) for g in op.gather]
+    op.n_runs = max(len(r) for r in runs)
+    op.runs = np.zeros((op.n_nodes, op.n_runs, 4), dtype=np.int32)
+    for nd_i, rl in enumerate(runs):
+        for r, (i0, f0, ln) in enumerate(rl):
+            op.runs[nd_i, r] = (i0, f0, ln, 0)
 
 
 OP_ID_POW = 7   # segment-only op code (csrc/layer.cuh): identity rows followed by |x|^p rows of the same inputs
@@ -824,7 +967,7 @@ def serialize(spec):
         n_w = 1 if op.shared else op.n_nodes
         n_terms = sum(ps["K"] for ps in op.passes)
         out.append(struct.pack("<12q", op.n_nodes, op.d_in, op.in_dim, op.out_dim, len(op.passes),
-                               int(op.shared) | (op.warps << 8),
+                               int(op.shared) | (op.warps << 8) | ((1 if op.engine == "tc" else 0) << 16),
                                op.n_rows, op.twc, op.alg_flops, op.exe_flops, op.npc, op.n_runs)
                    + struct.pack("<2d", float(op.clip[0]), float(op.clip[1]))
                    + struct.pack("<2q", op.param_floats, n_terms))
@@ -863,7 +1006,11 @@ def serialize(spec):
         out.append(_arr(params, np.float32))
         out.append(_arr(t16, np.int16))
         for ps, segs in zip(op.passes, seg_lists):
-            out.append(struct.pack("<16q", ps["K"], ps["Npad"], ps["NT"], ps["NTL"], ps["KS"], ps["TW"], ps["dst"],
+            if op.engine == "tc":
+                tile_fields = (op.tc["nd"], op.tc["nstx"], op.tc["nw"], op.tc["na"])
+            else:
+                tile_fields = (ps["NT"], ps["NTL"], ps["KS"], ps["TW"])
+            out.append(struct.pack("<16q", ps["K"], ps["Npad"], *tile_fields, ps["dst"],
                                    ps["row0"], ps["w_off"], ps["b_off"], ps["term_off"], len(segs), ps["K_real"],
                                    ps["N_real"], ps["SW"], 0))
             sb = b"".join(struct.pack("<3if4i", o, k0, k1, p, kind, ibase, nomean, 0)
@@ -878,6 +1025,14 @@ def describe(spec):
     lines = ["plan: %d -> %d, %d ops, %.3f MFLOP/window algorithmic, %.3f executed"
              % (spec.input_dim, spec.output_dim, len(spec.ops), spec.alg_flops / 1e6, spec.exe_flops / 1e6)]
     for k, op in enumerate(spec.ops):
+        if op.engine == "tc":
+            p, t = op.passes[0], op.tc
+            lines.append("  op%-2d nodes=%-4d d_in=%-4d out=%-5d %s %s tc [K%d->N%d pad %dx%d, %d chunks] twc=%d nd=%d nstx=%d nw=%d na=%d "
+                         "tmem=%d runs=%d smem=%dK"
+                         % (k, op.n_nodes, op.d_in, op.out_dim, "clone" if op.shared else "layer", op.mode, p["K_real"],
+                            p["N_real"], t["Kpad"], t["Npad16"], t["n_chunks"], op.twc, t["nd"], t["nstx"], t["nw"], t["na"],
+                            t["tmem_cols"], op.n_runs, t["smem"] // 1024))
+            continue
         ps = ", ".join("K%d->N%d(%dx%d sw%d ks%d tw%d)" % (p["K_real"], p["N_real"], p["NT"], p["NTL"], p["SW"], p["KS"], p["TW"])
                        for p in op.passes)
         lines.append("  op%-2d nodes=%-4d d_in=%-4d out=%-5d %s %s [%s] warps=%d twc=%d runs=%d rows=%d smem=%dK"

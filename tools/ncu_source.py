@@ -6,7 +6,7 @@ import sys
 
 
 def main(path, skip=0, top=40):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--kernel-name", "regex:layer_kernel",
+    raw = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--kernel-name", "regex:layer_",
                           "--launch-skip", str(skip), "--launch-count", "1"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     print(rows[0][:2])
