@@ -14,8 +14,9 @@ uniform integers 0..255, seed 12345600 (FaceDetectUpdated.py:146).  One step = o
   e2e   : the same through the public drop-in call GpuFlow.execute(x) with x in pinned HOST memory:
           host->device copy of the windows and device->host copy of the (N, 60) float64 features are
           inside the timed region
-  roofline : the fused layer kernels are FP32-FFMA bound; achieved =
-          algorithmic flops (hgsfa_plan_flops) / device time of the layer launches
+  roofline : dominant kernel of the step (DESIGN.md section 6): hgsfa::layer_tc_kernel (tcgen05 3xTF32) against
+          measured bf16 peak / 6, or hgsfa::layer_kernel (packed FP32 FMA) against the measured FFMA2 peak;
+          achieved = algorithmic flops of that kernel's ops / its CUDA-event time inside the timed steps
   cpu_baseline : the float64 numpy oracle (the reference cannot run: Python 2 + un-vendored mdp /
           cuicuilco) on a bounded sample on the box's host cores, BLAS threads = min(12, nproc)
           (FaceDetectUpdated.py:74)
@@ -75,6 +76,55 @@ def _traffic_per_window():
         return float(t["layer_dram_bytes_per_window"]), t["source"], float(t["layer_share_of_step"])
     except Exception:
         return None, None, None
+
+
+def _roofline(op_stats, steps, n, fl, kernel_ms_last, peaks, fp32_peak, fp32_src, traffic, tsrc, lshare):
+    """Roofline of the dominant kernel of a step.  The layer ops run on one of two kernels:
+    hgsfa::layer_tc_kernel (tcgen05, 3xTF32: three TF32 MMAs per algorithmic multiply-add block, TF32 at half the
+    bf16 rate -> ceiling = measured bf16 peak / 6 in algorithmic flops) and hgsfa::layer_kernel (packed FP32 FMA).
+    Times are CUDA-event totals per op over the timed steps, on the launching stream."""
+    eng = {}
+    for st in op_stats:
+        e = eng.setdefault(st["engine"], dict(ms=0.0, alg=0.0, exe=0.0, ops=0))
+        e["ms"] += st["ms"] / steps
+        e["alg"] += st["alg_flops"] * n
+        e["exe"] += st["exe_flops"] * n
+        e["ops"] += 1
+    for e in eng.values():
+        e["achieved"] = e["alg"] / (e["ms"] * 1e-3) / 1e12 if e["ms"] > 0 else None
+    bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    tc_peak = bf16 / 6.0
+    dom = max(eng, key=lambda k: eng[k]["ms"]) if eng else "ffma"
+    out = {}
+    if dom == "tc":
+        a = eng["tc"]["achieved"]
+        out = {"bound": "tensor", "achieved": a, "peak": tc_peak, "unit": "TFLOP/s", "frac": a / tc_peak if a else None,
+               "kernel": "hgsfa::layer_tc_kernel (%d of %d layer ops, %.1f of %.1f ms per step)"
+                         % (eng["tc"]["ops"], len(op_stats), eng["tc"]["ms"], kernel_ms_last),
+               "peak_source": "%s bf16 %s %.1f TFLOP/s / 6 (TF32 = bf16 / 2; 3xTF32 split = 3 MMAs per algorithmic block)"
+                              % (peaks["_source"], "sustained" if "bf16_tflops_sustained" in peaks else "burst", bf16),
+               "tensor_pipe_flops_per_step": eng["tc"]["exe"]}
+    else:
+        a = eng.get("ffma", {}).get("achieved")
+        out = {"bound": "fp32", "achieved": a, "peak": fp32_peak, "unit": "TFLOP/s", "frac": a / fp32_peak if a else None,
+               "kernel": "hgsfa::layer_kernel", "peak_source": fp32_src}
+    if "ffma" in eng and dom == "tc":
+        a = eng["ffma"]["achieved"]
+        out["ffma_kernel"] = {"kernel": "hgsfa::layer_kernel (%d ops, %.1f ms per step)" % (eng["ffma"]["ops"], eng["ffma"]["ms"]),
+                              "bound": "fp32", "achieved": a, "peak": fp32_peak, "frac": a / fp32_peak if a else None,
+                              "peak_source": fp32_src}
+    whole = fl["algorithmic"] / (kernel_ms_last * 1e-3) / 1e12 if kernel_ms_last > 0 else None
+    out.update({
+        "traffic": (traffic * n) if traffic else None, "traffic_unit": "DRAM bytes per step, all layer launches (ncu)",
+        "traffic_source": tsrc, "kernel_share_of_step_ncu": lshare,
+        "algorithmic_bytes_per_step": fl["min_bytes"],
+        "algorithmic_flops_per_window": fl["algorithmic"] / n,
+        "whole_step_algorithmic_tflops": whole, "kernel_ms_per_step": kernel_ms_last,
+        "per_op_ms": [round(st["ms"] / steps, 3) for st in op_stats],
+        "per_op_engine": [st["engine"] for st in op_stats],
+        "hbm_frac": (fl["min_bytes"] / (kernel_ms_last * 1e-3) / 1e9 / peaks["hbm_gbs"]) if kernel_ms_last > 0 else None,
+        "hbm_peak_source": peaks["_source"]})
+    return out
 
 
 class ClockSampler(object):
@@ -241,6 +291,7 @@ def main():
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize(dev)
+    g.profile(True)          # CUDA events around every layer launch of the timed steps (per-op device time)
     l0 = g.stats()["launches"]
     sampler = ClockSampler(local_rank)
     barrier()
@@ -258,6 +309,8 @@ def main():
     ms_total = e0.elapsed_time(e1)
     launches = g.stats()["launches"] - l0
     kernel_ms_last = g.stats()["last_ms"]      # device time of the last step's launches (plan events)
+    op_stats = g.op_stats()                    # per-op totals over the timed steps
+    g.profile(False)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -297,12 +350,11 @@ def main():
         fl = g.flops(n)
         fp32_peak, fp32_src = _fp32_peak()
         peaks = _peaks()
-        achieved_tflops = fl["algorithmic"] / (kernel_ms_last * 1e-3) / 1e12 if kernel_ms_last > 0 else None
         tpw, tsrc, lshare = _traffic_per_window()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32 (FFMA ops) / 3xtf32 with f32 accumulation (tensor-core ops)", "data": "synthetic",
             "config": {"workload": "configs[1]: U11L_64 (FaceCentering2-shaped synthetic HiGSFA flow) forward, "
                                    "%d windows x 4096 uint8 per GPU per step" % n,
                        "windows_per_gpu": n, "window_dim": g.input_dim, "features": F, "flow": FLOW_SPEC,
@@ -313,19 +365,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
-            "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": (achieved_tflops / fp32_peak) if achieved_tflops else None,
-                         "traffic": (tpw * n) if tpw else None, "traffic_unit": "bytes per step (all layer launches)",
-                         "traffic_source": tsrc, "kernel_share_of_step_ncu": lshare,
-                         "algorithmic_bytes_per_step": fl["min_bytes"],
-                         "kernel": "hgsfa::layer_kernel (all 11 layer launches of a step)",
-                         "algorithmic_flops_per_window": fl["algorithmic"] / n,
-                         "executed_flops_per_window": fl["executed"] / n,
-                         "kernel_ms_per_step": kernel_ms_last,
-                         "peak_source": fp32_src,
-                         "hbm_frac": (fl["min_bytes"] / (kernel_ms_last * 1e-3) / 1e9 / peaks["hbm_gbs"])
-                         if kernel_ms_last > 0 else None,
-                         "hbm_peak_source": peaks["_source"]},
+            "roofline": _roofline(op_stats, args.steps, n, fl, kernel_ms_last, peaks, fp32_peak, fp32_src, tpw, tsrc, lshare),
         }
         if not args.no_cpu_baseline:
             threads = min(12, os.cpu_count() or 1)

@@ -90,6 +90,14 @@ int hgsfa_plan_execute_device(hgsfa_plan_t plan, const void* d_x, int x_dtype, i
  * accumulated device time of the most recent execute (CUDA events on the plan's stream; ms) */
 int hgsfa_plan_stats(hgsfa_plan_t plan, int64_t* launches, double* last_ms);
 
+/* Per-operation device times (bench.py's roofline; not a reference interface).  hgsfa_plan_profile(plan, 1)
+ * makes every following execute bracket each layer launch with CUDA events; hgsfa_plan_op_stats waits for
+ * the work, adds the elapsed times to the per-op totals and returns them.  Arrays hold `capacity` entries
+ * (one per op, see hgsfa_plan_info); engine: 0 = FFMA kernel, 1 = tensor-core kernel; flops are per window. */
+int hgsfa_plan_profile(hgsfa_plan_t plan, int enable);
+int hgsfa_plan_op_stats(hgsfa_plan_t plan, int64_t capacity, double* ms, int32_t* engine, double* alg_flops,
+                        double* exe_flops);
+
 /* tuning knobs (0 keeps the default): windows per front-segment chunk / back-segment chunk */
 int hgsfa_plan_set_chunks(hgsfa_plan_t plan, int64_t front_chunk, int64_t back_chunk);
 

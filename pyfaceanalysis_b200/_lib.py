@@ -33,6 +33,8 @@ SYMBOLS = [
     ("hgsfa_plan_execute", _int, [_vp, _vp, _int, _i64, _i64, _vp, _int, _i64, _vp]),
     ("hgsfa_plan_execute_device", _int, [_vp, _vp, _int, _int, _i64, _i64, _vp, _int, _i64, _vp]),
     ("hgsfa_plan_stats", _int, [_vp, _pi64, _pd]),
+    ("hgsfa_plan_profile", _int, [_vp, _int]),
+    ("hgsfa_plan_op_stats", _int, [_vp, _i64, _pd, _vp, _pd, _pd]),
     ("hgsfa_plan_set_chunks", _int, [_vp, _i64, _i64]),
     ("hgsfa_crop_extent", _int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int, _int, _vp, _int, _int, _vp]),
     ("hgsfa_crop_extent_device", _int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int, _int, _vp, _int, _int, _vp]),

@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2,-Wall",
     "-I", os.path.join(ROOT, "include"),
-]
+] + (["-DHGSFA_TC_CK=" + os.environ["HGSFA_TC_CK"]] if "HGSFA_TC_CK" in os.environ else [])
 
 
 def nvcc_path():

@@ -147,7 +147,7 @@ static size_t layout_tc(TcOpDev& d, int n_segs, int el) {
   d.sm_chunkseg = (int)off;
   off += up(size_t(d.n_chunks + 1) * 4);
   d.sm_bias = (int)off;
-  off += up(size_t(2) * d.Npad16 * 4);
+  off += up(size_t(8) * d.Npad16 * 4);
   d.sm_raw_bytes = int(size_t(d.d_in) * TILE * el);
   d.sm_xstage_bytes = (int)up(size_t(d.twc) * d.sm_raw_bytes + size_t(d.head_floats) * 4);
   d.sm_x0 = (int)off;
@@ -217,6 +217,11 @@ struct hgsfa_plan_s {
   int sm_count = 148;
   int max_npc = 16;
   int max_npc_tc = 32;
+  // optional per-op timing (hgsfa_plan_profile)
+  bool profile = false;
+  struct Stamp { int op; cudaEvent_t e0, e1; };
+  std::vector<Stamp> stamps;
+  std::vector<double> op_ms;
 };
 
 namespace {
@@ -466,6 +471,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
             piece.kind = std::min(real, len);
             piece.ibase = ib;
             piece.pad1 = tk;
+            if (sgm.op == OP_TRI) { piece.ibase = sgm.ibase; piece.nomean = tk - sgm.k0; }
             tsegs.push_back(piece);
             if (ib >= 0) ib += len;
             tk += piece.kind;
@@ -484,6 +490,20 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
             b.op = OP_ABSPOW; b.k0 = sgm.k0 + half; b.nomean = 0;
             push(a); push(b);
           } else {
+            if (sgm.op == OP_MUL) {
+              // all products x_i x_j, r0 <= i <= j < r0 + n in row-major order (QT expansion)?  -> register-resident form
+              const int len = sgm.k1 - sgm.k0, r0 = terms[sgm.k0].i;
+              int n = 0;
+              for (int c = 3; c <= 16; ++c) if (c * (c + 1) / 2 == len) n = c;
+              bool tri = n > 0;
+              for (int q = 0; tri && q < len; ++q)
+                tri = terms[sgm.k0 + q].i == r0 + tri_row(n, q) && terms[sgm.k0 + q].j == r0 + tri_col(n, q);
+              if (tri && !getenv("HGSFA_TC_NO_TRI")) {
+                sgm.op = OP_TRI;
+                sgm.p = float(n);
+                sgm.ibase = r0;
+              }
+            }
             push(sgm);
           }
         }
@@ -702,9 +722,16 @@ int run_ops(hgsfa_plan_s* pl, int o0, int o1, const void* xin, bool xin_u8, floa
   for (int o = o0; o < o1; ++o) {
     OpHost& op = pl->ops[o];
     float* dst = (o == o1 - 1) ? final_out : static_cast<float*>(pp[(o - o0) & 1].p);
+    hgsfa_plan_s::Stamp stamp{o, nullptr, nullptr};
+    if (pl->profile && cudaEventCreate(&stamp.e0) == cudaSuccess && cudaEventCreate(&stamp.e1) == cudaSuccess)
+      cudaEventRecord(stamp.e0, st);
     int rc = op.tc ? (cur_u8 ? launch_layer_tc<uint8_t>(pl, op, cur, dst, ntiles, st) : launch_layer_tc<float>(pl, op, cur, dst, ntiles, st))
                    : (cur_u8 ? launch_layer<uint8_t>(pl, op, cur, dst, ntiles, st) : launch_layer<float>(pl, op, cur, dst, ntiles, st));
     if (rc) return rc;
+    if (pl->profile && stamp.e1) {
+      cudaEventRecord(stamp.e1, st);
+      pl->stamps.push_back(stamp);
+    }
     cur = dst;
     cur_u8 = false;
   }
@@ -712,6 +739,36 @@ int run_ops(hgsfa_plan_s* pl, int o0, int o1, const void* xin, bool xin_u8, floa
 }
 
 }  // namespace
+
+extern "C" int hgsfa_plan_profile(hgsfa_plan_t pl, int enable) {
+  HG_CHECK(pl, "hgsfa_plan_profile: null plan");
+  pl->profile = enable != 0;
+  pl->op_ms.assign(pl->ops.size(), 0.0);
+  return 0;
+}
+
+extern "C" int hgsfa_plan_op_stats(hgsfa_plan_t pl, int64_t capacity, double* ms, int32_t* engine, double* alg_flops,
+                                   double* exe_flops) {
+  HG_CHECK(pl, "hgsfa_plan_op_stats: null plan");
+  HG_CHECK(capacity >= (int64_t)pl->ops.size(), "hgsfa_plan_op_stats: capacity %lld < %zu ops", (long long)capacity, pl->ops.size());
+  DeviceGuard guard(pl->device);
+  HG_CUDA(cudaDeviceSynchronize());
+  pl->op_ms.resize(pl->ops.size(), 0.0);
+  for (auto& s : pl->stamps) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, s.e0, s.e1) == cudaSuccess) pl->op_ms[s.op] += t;
+    cudaEventDestroy(s.e0);
+    cudaEventDestroy(s.e1);
+  }
+  pl->stamps.clear();
+  for (size_t o = 0; o < pl->ops.size(); ++o) {
+    if (ms) ms[o] = pl->op_ms[o];
+    if (engine) engine[o] = pl->ops[o].tc ? 1 : 0;
+    if (alg_flops) alg_flops[o] = double(pl->ops[o].alg_flops);
+    if (exe_flops) exe_flops[o] = double(pl->ops[o].exe_flops);
+  }
+  return 0;
+}
 
 extern "C" int hgsfa_plan_execute_device(hgsfa_plan_t pl, const void* d_x, int x_dtype, int x_layout, int64_t n,
                                          int64_t ld, void* d_y, int y_dtype, int64_t y_cols, void* stream) {

@@ -24,7 +24,10 @@
 
 namespace hgsfa {
 
-constexpr int TC_CK = 32;            // terms per chunk (A stage = 32 hi + 32 lo columns)
+#ifndef HGSFA_TC_CK
+#define HGSFA_TC_CK 32
+#endif
+constexpr int TC_CK = HGSFA_TC_CK;   // terms per chunk (A stage = TC_CK hi + TC_CK lo columns)
 constexpr int TC_THREADS = 192;
 constexpr int TC_MAX_TW = 8;
 
@@ -55,18 +58,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // bounded wait: a protocol error traps (launch failure reported to the host) instead of hanging the GPU
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait_tc(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep in hardware instead of polling
         : "memory");
     if (ok) return;
+    if (BACKOFF) __nanosleep(64);      // producer: leave the issue slots to the expansion warps
   }
   __trap();
 }
@@ -141,6 +147,18 @@ __device__ __forceinline__ void tc_store8(uint32_t col_hi, const float (&v)[8]) 
   tmem_st8(col_hi + TC_CK, lo);
 }
 
+// values that are exactly representable in TF32 (uint8 pixels, identity terms): no split needed
+__device__ __forceinline__ void tc_store8_exact(uint32_t col_hi, const float (&v)[8]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hi[j] = __float_as_uint(v[j]);
+    lo[j] = 0u;
+  }
+  tmem_st8(col_hi, hi);
+  tmem_st8(col_hi + TC_CK, lo);
+}
+
 // one receptive-field value of this thread's window; xp already points at (row, window)
 template <typename IN_T>
 __device__ __forceinline__ float tc_ld(const IN_T* xp) {
@@ -152,30 +170,86 @@ __device__ __forceinline__ float tc_ld(const IN_T* xp) {
 // 1 identity, 2 |x|^p.  A segment occupies a multiple of 8 A columns; the terms past `cnt` are padding
 // (their weight rows are zero) and repeat the last real term so that the operand stays finite.
 template <typename IN_T, int MODE>
+__device__ __forceinline__ float tc_row_value(const IN_T* xp, const float* mp, int j, float p) {
+  float x = tc_ld<IN_T>(xp + j * TILE);
+  if (MODE != 0) x -= mp[j];
+  if (MODE == 2) x = abspow(x, p);
+  return x;
+}
+template <typename IN_T, int MODE>
 __device__ __forceinline__ void tc_seg_rows(const IN_T* xp, const float* mp, int cnt, int ngroups, float p, uint32_t col) {
+  // two groups (16 independent operand chains) per iteration while both are full: a warp issues in order, and
+  // with one expansion warp per scheduler and CTA the instruction-level parallelism has to come from here
 #pragma unroll 1
-  for (int g = 0; g < ngroups; ++g, cnt -= 8, xp += 8 * TILE, mp += 8, col += 8) {
+  for (; ngroups >= 2 && cnt >= 16; ngroups -= 2, cnt -= 16, xp += 16 * TILE, mp += 16, col += 16) {
+    float v0[8], v1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v0[j] = tc_row_value<IN_T, MODE>(xp, mp, j, p);
+      v1[j] = tc_row_value<IN_T, MODE>(xp, mp, 8 + j, p);
+    }
+    if (sizeof(IN_T) == 1 && MODE == 0) {
+      tc_store8_exact(col, v0);
+      tc_store8_exact(col + 8, v1);
+    } else {
+      tc_store8(col, v0);
+      tc_store8(col + 8, v1);
+    }
+  }
+#pragma unroll 1
+  for (; ngroups > 0; --ngroups, cnt -= 8, xp += 8 * TILE, mp += 8, col += 8) {
     float v[8];
     if (cnt >= 8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float x = tc_ld<IN_T>(xp + j * TILE);
-        if (MODE != 0) x -= mp[j];
-        if (MODE == 2) x = abspow(x, p);
-        v[j] = x;
-      }
+      for (int j = 0; j < 8; ++j) v[j] = tc_row_value<IN_T, MODE>(xp, mp, j, p);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int jj = min(j, cnt - 1);
-        float x = tc_ld<IN_T>(xp + jj * TILE);
-        if (MODE != 0) x -= mp[jj];
-        if (MODE == 2) x = abspow(x, p);
-        v[j] = x;
-      }
+      for (int j = 0; j < 8; ++j) v[j] = tc_row_value<IN_T, MODE>(xp, mp, min(j, cnt - 1), p);
     }
-    tc_store8(col, v);
+    if (sizeof(IN_T) == 1 && MODE == 0) tc_store8_exact(col, v);
+    else tc_store8(col, v);
   }
+}
+
+// Upper-triangular products x_i x_j (r0 <= i <= j < r0 + N, row-major: the QT expansion) of N centred rows.
+// The N operands are loaded once into registers; the enumeration is unrolled at compile time, so a term
+// costs one FMUL plus the TF32 split.  A piece covers the 8-term groups [t0 / 8, (t0 + cnt + 7) / 8).
+constexpr int OP_TRI = 9;            // segment-only op code: p = N, ibase = r0, nomean = t0
+__host__ __device__ constexpr int tri_row(int n, int idx) {
+  int i = 0, len = n;
+  while (idx >= len && len > 0) { idx -= len; --len; ++i; }
+  return i;
+}
+__host__ __device__ constexpr int tri_col(int n, int idx) {
+  int i = 0, len = n;
+  while (idx >= len && len > 0) { idx -= len; --len; ++i; }
+  return i + idx;
+}
+template <int N, int G>
+__device__ __forceinline__ void tc_tri_groups(const float (&xc)[N], int g0, int g1, uint32_t col) {
+  constexpr int T = N * (N + 1) / 2;
+  if constexpr (8 * G < T) {
+    if (G >= g0 && G < g1) {
+      float v[8];
+#define HG_TRI_TERM(J)                                                                       \
+  {                                                                                          \
+    constexpr int idx = 8 * G + J;                                                           \
+    if constexpr (idx < T) v[J] = xc[tri_row(N, idx)] * xc[tri_col(N, idx)];                 \
+    else v[J] = 0.f;                                                                         \
+  }
+      HG_TRI_TERM(0) HG_TRI_TERM(1) HG_TRI_TERM(2) HG_TRI_TERM(3) HG_TRI_TERM(4) HG_TRI_TERM(5) HG_TRI_TERM(6) HG_TRI_TERM(7)
+#undef HG_TRI_TERM
+      tc_store8(col + uint32_t(8 * (G - g0)), v);
+    }
+    tc_tri_groups<N, G + 1>(xc, g0, g1, col);
+  }
+}
+template <typename IN_T, int N>
+__device__ __forceinline__ void tc_seg_tri(const IN_T* xr, const float* mr, int t0, int cnt, uint32_t col) {
+  float xc[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) xc[i] = tc_ld<IN_T>(xr + i * TILE) - mr[i];
+  tc_tri_groups<N, 0>(xc, t0 >> 3, (t0 + cnt + 7) >> 3, col);
 }
 
 template <typename IN_T>
@@ -231,7 +305,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     Ring rx(nstx), rw(nw);
     for (int node = node_begin; node < node_end; ++node, rx.next()) {
       const int sx = rx.idx;
-      mbar_wait_tc(&bars[TCB_XFREE + sx], rx.par ^ 1u);
+      mbar_wait_tc<true>(&bars[TCB_XFREE + sx], rx.par ^ 1u);
       uint8_t* stage = smem + op.sm_x0 + size_t(sx) * op.sm_xstage_bytes;
       const Run* runs = op.runs + size_t(node) * op.n_runs;
       const int nwi = op.shared ? 0 : node;
@@ -258,7 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const float* wnode = op.wimg + size_t(nwi) * n_chunks * op.wchunk_floats;
       for (int c = 0; c < n_chunks; ++c, rw.next()) {
         const int sw = rw.idx;
-        mbar_wait_tc(&bars[TCB_WFREE + sw], rw.par ^ 1u);
+        mbar_wait_tc<true>(&bars[TCB_WFREE + sw], rw.par ^ 1u);
         if (lane == 0) {
           const uint32_t bytes = uint32_t(op.wchunk_floats) * 4u;
           mbar_expect_tx(&bars[TCB_WFULL + sw], bytes);
@@ -314,12 +388,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const Term16* terms = reinterpret_cast<const Term16*>(smem + op.sm_terms);
     const Seg* segs = reinterpret_cast<const Seg*>(smem + op.sm_segs);
     const int* chunk_seg = reinterpret_cast<const int*>(smem + op.sm_chunkseg);
-    float* bias_buf = reinterpret_cast<float*>(smem + op.sm_bias);   // [2][Npad16]
+    float* bias_buf = reinterpret_cast<float*>(smem + op.sm_bias);   // [4 warps][2 sets][Npad16]
 
     auto epilogue = [&](int node, int set, uint32_t par) {
       const int nvalid = __ldg(op.n_valid + node);
       const int col0 = __ldg(op.out_col + node) + __ldg(op.col_off + node);
-      const float* bias = bias_buf + set * op.Npad16;
+      const float* bias = bias_buf + (warp * 2 + set) * op.Npad16;
       for (int t = 0; t < vt; ++t) {
         mbar_wait_tc(&bars[TCB_DFULL + set * TC_MAX_TW + t], par);
         tc_fence_after();
@@ -335,15 +409,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (lane == 0) mbar_arrive(&bars[TCB_DFREE + set * TC_MAX_TW + t]);
           }
           const int nleft = nvalid - n0;
+          float y[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + 4 * q);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            y[4 * q + 0] = fminf(fmaxf(__uint_as_float(v[4 * q + 0]) + b4.x, clo), chi);
+            y[4 * q + 1] = fminf(fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, clo), chi);
+            y[4 * q + 2] = fminf(fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, clo), chi);
+            y[4 * q + 3] = fminf(fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, clo), chi);
+          }
+          if (nleft >= 16) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const int j = 4 * q + r;
-              if (j < nleft) out[j * TILE] = fminf(fmaxf(__uint_as_float(v[j]) + bb[r], clo), chi);
-            }
+            for (int j = 0; j < 16; ++j) out[j * TILE] = y[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nleft) out[j * TILE] = y[j];
           }
         }
       }
@@ -360,9 +441,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const float* mean = head;
       const int d_pad = (op.d_in + 3) & ~3;
       // bias of this node, kept past the release of the stage (the epilogue may run one node later)
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // epilogue readers of the previous use of this slot are done
-      if (tid < op.Npad16) bias_buf[rd.idx * op.Npad16 + tid] = head[d_pad + tid];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // (each warp keeps its own copy: no barrier between the four expansion warps)
+      __syncwarp();
+      for (int i = lane; i < op.Npad16; i += 32) bias_buf[(warp * 2 + rd.idx) * op.Npad16 + i] = head[d_pad + i];
+      __syncwarp();
 
       for (int c = 0; c < n_chunks; ++c) {
         const int sg0 = chunk_seg[c], sg1 = chunk_seg[c + 1];
@@ -382,6 +464,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               if (sg.op == OP_ABSPOW) tc_seg_rows<IN_T, 2>(xp, mp, cnt, ngroups, sg.p, col);
               else if (sg.nomean) tc_seg_rows<IN_T, 0>(xp, mp, cnt, ngroups, 0.f, col);
               else tc_seg_rows<IN_T, 1>(xp, mp, cnt, ngroups, 0.f, col);
+              continue;
+            }
+            if (sg.op == OP_TRI) {
+              const IN_T* xr = xs + size_t(sg.ibase) * TILE + tid;
+              const float* mr = mean + sg.ibase;
+              switch (int(sg.p)) {
+#define HG_TRI(N_) case N_: tc_seg_tri<IN_T, N_>(xr, mr, sg.nomean, cnt, col); break;
+                HG_TRI(3) HG_TRI(4) HG_TRI(5) HG_TRI(6) HG_TRI(7) HG_TRI(8) HG_TRI(9) HG_TRI(10) HG_TRI(11) HG_TRI(12)
+                HG_TRI(13) HG_TRI(14) HG_TRI(15) HG_TRI(16)
+#undef HG_TRI
+                default: break;
+              }
               continue;
             }
             const Term16* tp = terms + sg.pad1;                           // pad1 = first entry of the term table

@@ -142,6 +142,18 @@ class GpuFlow(object):
         _lib.check(_lib.load().hgsfa_plan_stats(self._handle, C.byref(launches), C.byref(ms)))
         return dict(launches=launches.value, last_ms=ms.value)
 
+    def profile(self, enable=True):
+        """Bracket every layer launch of the following executes with CUDA events (see ``op_stats``)."""
+        _lib.check(_lib.load().hgsfa_plan_profile(self._handle, int(bool(enable))))
+
+    def op_stats(self):
+        """Per-op totals since ``profile(True)``: list of dict(ms, engine, alg_flops, exe_flops) (flops per window)."""
+        n = len(self.spec.ops)
+        ms, alg, exe = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        eng = (C.c_int32 * n)()
+        _lib.check(_lib.load().hgsfa_plan_op_stats(self._handle, n, ms, C.cast(eng, C.c_void_p), alg, exe))
+        return [dict(ms=ms[i], engine="tc" if eng[i] else "ffma", alg_flops=alg[i], exe_flops=exe[i]) for i in range(n)]
+
     def set_chunks(self, front=0, back=0):
         _lib.check(_lib.load().hgsfa_plan_set_chunks(self._handle, int(front), int(back)))
 

@@ -622,14 +622,16 @@ def _decompose(op):
             op.runs[nd, r] = (i0, f0, ln, 0)
 
 
-# "auto": ops with at least TC_MIN_K expansion terms per node run on the tensor cores (tcgen05, 3xTF32), smaller
-# ones on the FFMA kernel (measured cross-over, profiles/README_r01.md); "tc" / "ffma" force one engine
+# "auto": single-pass ops with at least TC_MIN_K expansion terms per node run on the tensor cores (tcgen05, 3xTF32),
+# the rest (gather-only ops, anything the tensor-core kernel does not take) on the FFMA kernel; "ffma" forces the
+# FP32 kernel everywhere (7.5e-6 x std instead of 1.7e-4 x std against the float64 oracle, 1.5x slower).
+# Measured on U11L_64 (profiles/README_r01.md): all ops on tcgen05 39.4 ms, first two layers on FFMA 41.1 ms.
 ENGINE = _os.environ.get("HGSFA_ENGINE", "auto")
-TC_MIN_K = int(_os.environ.get("HGSFA_TC_MIN_K", "64"))
-TC_CK = 32          # terms per chunk (csrc/layer_tc.cuh)
+TC_MIN_K = int(_os.environ.get("HGSFA_TC_MIN_K", "0"))
+TC_CK = int(_os.environ.get("HGSFA_TC_CK", "32"))          # terms per chunk (csrc/layer_tc.cuh, compile-time constant there)
 # two CTAs per SM (256 tensor-memory columns, 113 KB each): measured 56.8 vs 87.8 ms per 1M windows against one big CTA
-TC_MAX_COLS = int(_os.environ.get("HGSFA_TC_MAXCOLS", "256"))
-TC_MAX_SMEM = int(_os.environ.get("HGSFA_TC_MAXSMEM", "113")) * 1024
+TC_TIERS = [(int(a), int(b) * 1024) for a, b in
+            (t.split(":") for t in _os.environ.get("HGSFA_TC_TIERS", "256:113,512:227").split(","))]   # (columns, KB) per CTA
 
 
 def _tc_eligible(op):
@@ -684,12 +686,12 @@ def _decompose_tc(op):
 
     def up(x):
         return (x + 127) // 128 * 128
-    fixed = 512 + 2 * up(K * 8) + up(len(segs) * 32) + up((n_chunks + 1) * 4) + up(2 * npad16 * 4)
+    fixed = 512 + 2 * up(K * 8) + up(len(segs) * 32) + up((n_chunks + 1) * 4) + up(8 * npad16 * 4)
     t_mma = 3.0 * (kpad / 8.0) * (17.0 + 0.2 * npad16)          # ns per (node, tile)
     best = None
     forced = {k: int(_os.environ[e]) for k, e in (("twc", "HGSFA_TC_TWC"), ("nd", "HGSFA_TC_ND"), ("nstx", "HGSFA_TC_NSTX"),
                                                   ("na", "HGSFA_TC_NA"), ("nw", "HGSFA_TC_NW")) if e in _os.environ}
-    for max_cols, max_smem in ((TC_MAX_COLS, TC_MAX_SMEM), (512, SMEM_LIMIT)):
+    for max_cols, max_smem in TC_TIERS:
       if best is not None:
         break
       for twc in range(1, 9):
