@@ -58,7 +58,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // bounded wait: a protocol error traps (launch failure reported to the host) instead of hanging the GPU
-template <bool BACKOFF = false>
+template <int SLEEP_NS = 32>
 __device__ __forceinline__ void mbar_wait_tc(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
 #pragma unroll 1
@@ -72,7 +72,7 @@ __device__ __forceinline__ void mbar_wait_tc(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep in hardware instead of polling
         : "memory");
     if (ok) return;
-    if (BACKOFF) __nanosleep(64);      // producer: leave the issue slots to the expansion warps
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);      // a waiting warp must not eat the issue slots of the working ones
   }
   __trap();
 }
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     Ring rx(nstx), rw(nw);
     for (int node = node_begin; node < node_end; ++node, rx.next()) {
       const int sx = rx.idx;
-      mbar_wait_tc<true>(&bars[TCB_XFREE + sx], rx.par ^ 1u);
+      mbar_wait_tc<256>(&bars[TCB_XFREE + sx], rx.par ^ 1u);
       uint8_t* stage = smem + op.sm_x0 + size_t(sx) * op.sm_xstage_bytes;
       const Run* runs = op.runs + size_t(node) * op.n_runs;
       const int nwi = op.shared ? 0 : node;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const float* wnode = op.wimg + size_t(nwi) * n_chunks * op.wchunk_floats;
       for (int c = 0; c < n_chunks; ++c, rw.next()) {
         const int sw = rw.idx;
-        mbar_wait_tc<true>(&bars[TCB_WFREE + sw], rw.par ^ 1u);
+        mbar_wait_tc<256>(&bars[TCB_WFREE + sw], rw.par ^ 1u);
         if (lane == 0) {
           const uint32_t bytes = uint32_t(op.wchunk_floats) * 4u;
           mbar_expect_tx(&bars[TCB_WFULL + sw], bytes);

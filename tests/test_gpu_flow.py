@@ -57,6 +57,23 @@ def test_u11l_parity_in_distribution(u11l_flow):
     g.close()
 
 
+@pytest.mark.parametrize("engine", ["ffma", "tc"])
+def test_u11l_both_engines(u11l_flow, engine, monkeypatch):
+    """The packed-FP32 kernel and the tcgen05 3xTF32 kernel both meet the tolerance, and agree with each other."""
+    from pyfaceanalysis_b200 import GpuFlow, plan, synthetic
+    monkeypatch.setattr(plan, "ENGINE", engine)
+    g = GpuFlow(u11l_flow)
+    assert {op.engine for op in g.spec.ops} == {engine}
+    x = synthetic.synthetic_patches(384, (64, 64), 21)
+    e = _check(g, u11l_flow, x, std=u11l_flow._train_output_std, tol=(2e-5 if engine == "ffma" else TOL))
+    print("U11L_64 engine", engine, "max err/std", e)
+    g.profile(True)
+    g.execute(x)
+    st = g.op_stats()
+    assert len(st) == 11 and all(s["engine"] == engine and s["ms"] > 0 for s in st)
+    g.close()
+
+
 def test_u11l_parity_uniform_noise(u11l_flow):
     """BASELINE config 2 input: uniform integer pixels 0..255 (far outside the fitted distribution; the
     inter-layer saturation keeps the network finite)."""

@@ -174,3 +174,28 @@ def test_tile_choice_and_segments():
     fused = plan._fuse_id_pow(segs)
     assert fused[0][0] == plan.OP_ID_POW and fused[0][1:3] == (0, 12) and len(fused) == 2
     assert plan._gather_runs([4, 5, 6, 10, 11, 3]) == [(0, 4, 3), (3, 10, 2), (5, 3, 1)]
+
+
+def test_tensor_core_configuration(u11l_flow, monkeypatch):
+    """Tensor-core ops: 8-aligned segments, tensor-memory columns and shared memory inside the hardware budgets."""
+    monkeypatch.setattr(plan, "ENGINE", "auto")
+    spec = plan.compile_flow(u11l_flow)
+    assert all(op.engine == "tc" for op in spec.ops)
+    for op in spec.ops:
+        t, ps = op.tc, op.passes[0]
+        assert t["Kpad"] % 8 == 0 and t["Kpad"] >= ps["K"] and t["Npad16"] % 16 == 0 and t["Npad16"] >= ps["N_real"]
+        cols = t["nd"] * op.twc * t["Npad16"] + t["na"] * 2 * plan.TC_CK
+        assert cols <= t["tmem_cols"] <= 512 and t["smem"] <= plan.SMEM_LIMIT and 1 <= op.twc <= 8
+        assert t["n_chunks"] == -(-t["Kpad"] // plan.TC_CK)
+    pieces, kpad = plan._tc_segments([(ex.OP_ID, 0, 26, 0.0, 0, 0), (ex.OP_ABSPOW, 26, 52, 0.8, 0, 0)], 52)
+    assert kpad == 64 and [(a, b) for _, a, b in pieces] == [(0, 32), (32, 64)]
+    pieces, kpad = plan._tc_segments([(plan.OP_ID_POW, 0, 108, 0.8, 0, 0), (ex.OP_MUL, 108, 163, 0.0, 0, -1)], 163)
+    assert kpad == 168 and all(a % 8 == 0 and b % 8 == 0 and a // plan.TC_CK == (b - 1) // plan.TC_CK for _, a, b in pieces)
+    # the numpy plan interpreter does not care about the engine: same algebra
+    x = synthetic.synthetic_patches(8, (64, 64), 5).astype(np.float64)
+    monkeypatch.setattr(plan, "ENGINE", "ffma")
+    spec_f = plan.compile_flow(u11l_flow)
+    assert all(op.engine == "ffma" for op in spec_f.ops)
+    assert np.allclose(plan_interp.run_plan(spec, x), plan_interp.run_plan(spec_f, x), rtol=1e-9, atol=1e-9)
+    blob = plan.serialize(spec)
+    assert (struct.unpack_from("<q", blob, 64 + 5 * 8)[0] >> 16) & 0xff == 1        # engine flag of op 0
