@@ -24,6 +24,8 @@ What is NOT here yet: the age / race / gender stage (``normaliz
 from __future__ import annotations
 
 import ctypes as C
+import os
+import time
 
 import numpy as np
 
@@ -82,16 +84,24 @@ def purge_detections(det, weight_confidences_by_area=True):
         de = np.sqrt(((b[0:2] - b[2:4]) ** 2).sum())
         return max(dl, dr) / de
 
-    unique = [det[0]]
+    del rel_err        # the loop below is its vectorised form: same operations in the same order per pair
+    unique = np.empty_like(det)
+    unique[0] = det[0]
+    n_u = 1
     for row in det:
-        min_d = 10000
-        for row2 in unique:
-            e = rel_err(row[5:9], row2[5:9])
-            if e < min_d:
-                min_d = e
+        u = unique[:n_u, 5:9]
+        dl = np.sqrt(((u[:, 0:2] - row[5:7]) ** 2).sum(axis=1))
+        dr = np.sqrt(((u[:, 2:4] - row[7:9]) ** 2).sum(axis=1))
+        de = np.sqrt(((u[:, 0:2] - u[:, 2:4]) ** 2).sum(axis=1))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            e = np.maximum(dl, dr) / de
+        # the reference keeps the running minimum with "<": NaN never replaces it
+        e = e[~np.isnan(e)]
+        min_d = min(10000, e.min()) if len(e) else 10000
         if min_d > 0.25:
-            unique.append(row)
-    return np.asarray(unique)
+            unique[n_u] = row
+            n_u += 1
+    return unique[:n_u].copy()
 
 
 class FaceDetector(object):
@@ -176,6 +186,21 @@ class FaceDetector(object):
         box[:, 3] = box[:, 3] - dy
         return box, too_far
 
+    def _pyramid(self, im_width, im_height, smallest_face):
+        """Window pyramid of one image size (host arrays + device copies), cached: it depends on the size only."""
+        key = (int(im_width), int(im_height), float(smallest_face))
+        cache = self.__dict__.setdefault("_pyramid_cache", {})
+        p = cache.get(key)
+        if p is None:
+            p = grid.window_pyramid(im_width, im_height, self.header, smallest_face,
+                                    self.cfg["patch_overlap_sampling"], self.cfg["patch_overlap_posx_posy"])
+            p["coords_dev"] = self.torch.as_tensor(p["coords"], device=self.dev)
+            p["patch_wh_dev"] = self.torch.as_tensor(p["patch_wh"], device=self.dev)
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = p
+        return p
+
     def detect(self, images, smallest_face=0.2, return_trace=False):
         """images: list of 2-D uint8 arrays (the reference's mode-'L' image, already prescaled).
         Returns a list (one entry per image) of (M,10) float64 detection arrays after the purge; with
@@ -186,31 +211,37 @@ class FaceDetector(object):
         net_Dx, net_Dy, net_Dang, net_mins, net_maxs, sw, sh, rw, rh = self.header
         stream = torch.cuda.current_stream(dev).cuda_stream
         sp = C.c_void_p(stream) if stream else None
+        prof = {} if os.environ.get("HGSFA_DETECT_PROFILE") else None      # phase -> seconds (synchronising: diagnostics only)
+        t_last = [time.perf_counter()]
+
+        def mark(name):
+            if prof is not None:
+                torch.cuda.synchronize(dev)
+                now = time.perf_counter()
+                prof[name] = prof.get(name, 0.0) + now - t_last[0]
+                t_last[0] = now
 
         # ---- window pyramid of every image, one batch ----
-        pyr = [grid.window_pyramid(im.shape[1], im.shape[0], self.header, smallest_face,
-                                   self.cfg["patch_overlap_sampling"], self.cfg["patch_overlap_posx_posy"])
-               for im in images]
+        pyr = [self._pyramid(im.shape[1], im.shape[0], smallest_face) for im in images]
         n0 = int(sum(len(p["coords"]) for p in pyr))
         counts = np.zeros(len(self.types), dtype=np.int64)
         if n0 == 0:
             out = [np.zeros((0, 10)) for _ in images]
             return (out, dict(stage_counts=counts, raw=[np.zeros((0, 10)) for _ in images])) if return_trace else out
-        coords_h = np.concatenate([p["coords"] for p in pyr])
-        wh_h = np.concatenate([p["patch_wh"] for p in pyr])
-        img_h = np.concatenate([np.full(len(p["coords"]), k, dtype=np.int32) for k, p in enumerate(pyr)])
         scale_h = np.concatenate([p["scale"] for p in pyr])
 
         imgs_dev = [torch.as_tensor(np.ascontiguousarray(im, dtype=np.uint8), device=dev) for im in images]
         img_ptrs = torch.tensor([t.data_ptr() for t in imgs_dev], dtype=torch.int64, device=dev)
         img_hw = torch.tensor([[t.shape[0], t.shape[1]] for t in imgs_dev], dtype=torch.int32, device=dev)
 
-        orig_coords = torch.as_tensor(coords_h, device=dev)
+        # per-window arrays are replicated on the device from the cached per-size pyramids: no per-window upload
+        orig_coords = torch.cat([p["coords_dev"] for p in pyr]) if len(pyr) > 1 else pyr[0]["coords_dev"].clone()
         orig_angles = torch.zeros(n0, dtype=torch.float64, device=dev)
-        patch_wh = torch.as_tensor(wh_h, device=dev)
+        patch_wh = torch.cat([p["patch_wh_dev"] for p in pyr]) if len(pyr) > 1 else pyr[0]["patch_wh_dev"]
         coords = orig_coords.clone()
         angles = orig_angles.clone()
-        img_idx = torch.as_tensor(img_h, device=dev)
+        img_idx = torch.repeat_interleave(torch.arange(len(pyr), dtype=torch.int32, device=dev),
+                                          torch.tensor([len(p["coords"]) for p in pyr], device=dev), output_size=n0)
         orig_idx = torch.arange(n0, dtype=torch.int32, device=dev)
         conf = torch.zeros(n0, dtype=torch.float64, device=dev)
         keep = torch.empty(n0, dtype=torch.uint8, device=dev)
@@ -223,6 +254,7 @@ class FaceDetector(object):
         min_r = net_mins / 0.825
         max_r = net_maxs / 0.825
 
+        mark("pyramid+upload")
         for k, full_type in enumerate(self.types):
             counts[k] = n
             if n == 0:
@@ -238,7 +270,9 @@ class FaceDetector(object):
                     C.c_void_p(img_ptrs.data_ptr()), C.c_void_p(img_hw.data_ptr()), C.c_void_p(img_idx.data_ptr()),
                     C.c_void_p(coords.data_ptr()), C.c_void_p(angles.data_ptr()), n, sw, sh, self.interpolation,
                     C.c_void_p(patches.data_ptr()), _lib.U8, _lib.TILED, sp))
+                mark("crop[%d]" % min(k, 1))
                 sl = net.execute_torch(patches, layout=_lib.TILED, n=n)
+                mark("flow[%d]" % min(k, 1))
             elif sl is None:
                 raise ValueError("stage %s reuses features but none were computed" % full_type)
             reg = self._regress(clf, sl, n, sp)
@@ -256,6 +290,7 @@ class FaceDetector(object):
                                                       C.c_void_p(count_dev.data_ptr()), C.c_void_p(scratch.data_ptr()),
                                                       scratch.numel(), sp))
             n_new = int(count_dev.item())          # the one host round trip of the stage
+            mark("head+update+compact[%d]" % min(k, 1))
             if n_new < n:
                 def gather(t, row_bytes):
                     out = torch.empty((n_new,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
@@ -270,6 +305,7 @@ class FaceDetector(object):
                 conf = gather(conf, 8)
                 sl = gather(sl.contiguous(), sl.shape[1] * 4)
                 n = n_new
+                mark("gather[%d]" % min(k, 1))
 
         # ---- survivors -> eyes -> detections (host arithmetic on dozens of rows, device compute for the eye flow) ----
         boxes = coords[:n].cpu().numpy()
@@ -279,8 +315,11 @@ class FaceDetector(object):
         scale_of = scale_h[orig_idx[:n].cpu().numpy()] if n else np.zeros(0, dtype=np.int32)
         if n and self.eye_net is not None:
             _, boxL, boxR = approximate_eye_boxes(boxes, ang)
-            eyesL_box, farL = self._find_eyes(img_ptrs, img_hw, img_idx[:n].contiguous(), angles[:n].contiguous(), ang, boxL, sp)
-            eyesR_box, farR = self._find_eyes(img_ptrs, img_hw, img_idx[:n].contiguous(), angles[:n].contiguous(), ang, boxR, sp)
+            # left and right eye patches of all faces in one batch (per-window work: identical results, half the launches)
+            both_box, both_far = self._find_eyes(img_ptrs, img_hw, torch.cat([img_idx[:n], img_idx[:n]]),
+                                                 torch.cat([angles[:n], angles[:n]]), np.concatenate([ang, ang]),
+                                                 np.concatenate([boxL, boxR]), sp)
+            eyesL_box, farL, eyesR_box, farR = both_box[:n], both_far[:n], both_box[n:], both_far[n:]
             ok = ~(farL | farR)
             eyes = np.concatenate([(eyesL_box[:, 0:2] + eyesL_box[:, 2:4]) / 2.0,
                                    (eyesR_box[:, 0:2] + eyesR_box[:, 2:4]) / 2.0], axis=1)[ok]
@@ -302,9 +341,13 @@ class FaceDetector(object):
             n = len(boxes)
         else:
             eyes = approximate_eye_coordinates(boxes, ang) if n else np.zeros((0, 4))
+        mark("eyes")
         raw = np.concatenate([boxes, ang[:, None], eyes, cf[:, None]], axis=1) if n else np.zeros((0, 10))
         per_image_raw = [raw[im_of == k] for k in range(len(images))]
         result = [purge_detections(r) if len(r) else np.zeros((0, 10)) for r in per_image_raw]
+        mark("purge")
+        if prof is not None:
+            self.last_profile = prof
         if return_trace:
             return result, dict(stage_counts=counts, raw=per_image_raw, n_windows=n0, disc_scores=disc_scores)
         return result

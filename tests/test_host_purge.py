@@ -1,0 +1,22 @@
+"""Host-side purge (reference face_analysis.py:186-221): vectorised form == the oracle's loop form."""
+import numpy as np
+
+from oracle import controller as ctl
+from pyfaceanalysis_b200.cascade import purge_detections
+
+
+def test_purge_matches_oracle_loop():
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 2, 7, 40):
+        det = np.zeros((n, 10))
+        c = rng.uniform(50, 400, size=(n, 2))
+        c[n // 2:] = c[:n - n // 2] + rng.normal(0, 2.0, size=(n - n // 2, 2))     # near-duplicates
+        half = rng.uniform(10, 40, size=n)
+        det[:, 0:2], det[:, 2:4] = c - half[:, None], c + half[:, None]
+        det[:, 4] = rng.uniform(-20, 20, size=n)
+        det[:, 5:7] = c + np.stack([-0.37 * half, -0.25 * half], axis=1)
+        det[:, 7:9] = c + np.stack([0.37 * half, -0.25 * half], axis=1)
+        det[:, 9] = rng.uniform(0, 0.5, size=n)
+        got = purge_detections(det)
+        ref = np.array(ctl.purge([r for r in det])).reshape(-1, 10) if n else np.zeros((0, 10))
+        assert got.shape == ref.shape and np.array_equal(got, ref)

@@ -68,6 +68,13 @@ def main():
            "images": args.images, "image_size": [1000, 562], "smallest_face": args.smallest_face,
            "windows_per_batch": int(tr["n_windows"]), "stage_counts": [int(c) for c in tr["stage_counts"]],
            "detections": int(sum(len(o) for o in out)), "calibrated_cut_offs": cut, "models": "synthetic " + args.spec + " cascade (tests/cascade_models.py)"}
+    if os.environ.get("HGSFA_DETECT_PROFILE"):
+        det.detect(images, smallest_face=args.smallest_face)
+        res["phase_ms"] = {k: round(v * 1e3, 2) for k, v in det.last_profile.items()}
+        print(json.dumps(res["phase_ms"]), file=sys.stderr)
+    if args.cpu_images <= 0:
+        print(json.dumps(res))
+        return
     threads = min(12, os.cpu_count() or 1)
     with threadpool_limits(limits=threads):
         t0 = time.perf_counter()
