@@ -84,24 +84,24 @@ def purge_detections(det, weight_confidences_by_area=True):
         de = np.sqrt(((b[0:2] - b[2:4]) ** 2).sum())
         return max(dl, dr) / de
 
-    del rel_err        # the loop below is its vectorised form: same operations in the same order per pair
-    unique = np.empty_like(det)
-    unique[0] = det[0]
-    n_u = 1
-    for row in det:
-        u = unique[:n_u, 5:9]
-        dl = np.sqrt(((u[:, 0:2] - row[5:7]) ** 2).sum(axis=1))
-        dr = np.sqrt(((u[:, 2:4] - row[7:9]) ** 2).sum(axis=1))
-        de = np.sqrt(((u[:, 0:2] - u[:, 2:4]) ** 2).sum(axis=1))
-        with np.errstate(divide="ignore", invalid="ignore"):
-            e = np.maximum(dl, dr) / de
-        # the reference keeps the running minimum with "<": NaN never replaces it
-        e = e[~np.isnan(e)]
-        min_d = min(10000, e.min()) if len(e) else 10000
+    del rel_err        # below: its vectorised form, the same operations in the same order for every pair
+    # e[i, j] = rel_err(row_i, row_j) for all pairs at once, then the reference's greedy scan over plain floats
+    eye = det[:, 5:9]
+    dl = np.sqrt(((eye[None, :, 0:2] - eye[:, None, 0:2]) ** 2).sum(axis=2))
+    dr = np.sqrt(((eye[None, :, 2:4] - eye[:, None, 2:4]) ** 2).sum(axis=2))
+    de = np.sqrt(((eye[:, 0:2] - eye[:, 2:4]) ** 2).sum(axis=1))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e = (np.maximum(dl, dr) / de[None, :]).tolist()
+    unique = [0]
+    for i in range(len(det)):
+        row_e = e[i]
+        min_d = 10000
+        for j in unique:
+            if row_e[j] < min_d:          # NaN never replaces the running minimum, as in the reference
+                min_d = row_e[j]
         if min_d > 0.25:
-            unique[n_u] = row
-            n_u += 1
-    return unique[:n_u].copy()
+            unique.append(i)
+    return det[unique].copy()
 
 
 class FaceDetector(object):
