@@ -168,3 +168,26 @@ def test_age_like_96x96_flow_and_real_heads(u11l96_flow, classifiers):
             assert np.allclose(got, exp, rtol=1e-9, atol=1e-9, equal_nan=True)
         h.close()
     g.close()
+
+
+@pytest.mark.parametrize("engine", ["ffma", "tc"])
+def test_exotic_expansions_both_engines(engine, monkeypatch):
+    """Term kinds the synthetic networks do not use: table products that are not a full triangle, triple
+    products, signed powers, |x| -- the generic paths of both kernels."""
+    import test_plan as tp
+    from pyfaceanalysis_b200 import GpuFlow, expansions as ex, plan
+    monkeypatch.setattr(plan, "ENGINE", engine)
+    rng = np.random.default_rng(12)
+    d, n_nodes, m = 12, 5, 7
+    funcs = ["identity", "signed_08expo", "pair_prod_adj2_ex", "s3CT", "abs", "s4QT", "unsigned_06expo"]
+    D = ex.expanded_dim(funcs, m)
+    conn = rng.permutation(n_nodes * d)
+    flow = [tp._sb(conn, n_nodes * d), tp._layer([tp._pca(d, m, rng) for _ in range(n_nodes)]),
+            tp._layer([tp._exp(m, funcs) for _ in range(n_nodes)]), tp._layer([tp._sfa(D, 6, rng) for _ in range(n_nodes)])]
+    g = GpuFlow(flow, input_dim=n_nodes * d)
+    assert g.spec.ops[-1].engine == engine
+    x = (rng.standard_normal((333, n_nodes * d)) * 2).astype(np.float32)
+    ref = onodes.flow_execute(flow, x.astype(np.float64))
+    y = g.execute(x)
+    assert np.abs(y - ref).max() <= 1e-3 * max(1.0, np.abs(ref).std()), np.abs(y - ref).max()
+    g.close()
