@@ -630,6 +630,7 @@ ENGINE = _os.environ.get("HGSFA_ENGINE", "auto")
 TC_MIN_K = int(_os.environ.get("HGSFA_TC_MIN_K", "0"))
 TC_CK = int(_os.environ.get("HGSFA_TC_CK", "32"))          # terms per chunk (csrc/layer_tc.cuh, compile-time constant there)
 # two CTAs per SM (256 tensor-memory columns, 113 KB each): measured 56.8 vs 87.8 ms per 1M windows against one big CTA
+TC_NA_CHOICES = tuple(int(v) for v in _os.environ.get("HGSFA_TC_NA_CHOICES", "2,4").split(","))
 TC_TIERS = [(int(a), int(b) * 1024) for a, b in
             (t.split(":") for t in _os.environ.get("HGSFA_TC_TIERS", "256:113,512:227").split(","))]   # (columns, KB) per CTA
 
@@ -691,12 +692,15 @@ def _decompose_tc(op):
     best = None
     forced = {k: int(_os.environ[e]) for k, e in (("twc", "HGSFA_TC_TWC"), ("nd", "HGSFA_TC_ND"), ("nstx", "HGSFA_TC_NSTX"),
                                                   ("na", "HGSFA_TC_NA"), ("nw", "HGSFA_TC_NW")) if e in _os.environ}
-    for max_cols, max_smem in TC_TIERS:
+    # single-chunk ops (K <= 32: per-item hand-overs dominate) do best with one A stage and three small CTAs per
+    # SM (measured on U11L_64 layer 0: 9.1 -> 8.3 ms); everything else with two A stages and two CTAs per SM
+    tiers = ([(128, 75 * 1024, (1,))] if n_chunks == 1 and not forced else []) + [(c, m, TC_NA_CHOICES) for c, m in TC_TIERS]
+    for max_cols, max_smem, na_choices in tiers:
       if best is not None:
         break
       for twc in range(1, 9):
         for nd in (1, 2):
-            for na in (2, 4):
+            for na in na_choices:
                 cols = nd * twc * npad16 + na * 2 * TC_CK
                 if cols > 512:
                     continue
@@ -715,7 +719,7 @@ def _decompose_tc(op):
                         if nd == 1:
                             t += 500.0 / twc                                          # MMA pipe drained before the epilogue
                         t += 300.0 / twc                                              # per-node hand-overs
-                        t += (0.0 if na == 4 else 0.05 * t_mma) + (0.0 if nw >= 3 else 0.03 * t_mma)
+                        t += (0.0 if na == 4 else (0.05 if na == 2 else 0.5) * t_mma) + (0.0 if nw >= 3 else 0.03 * t_mma)
                         key = (t, smem)
                         if best is None or key < best[0]:
                             best = (key, cfg, cols, smem)
