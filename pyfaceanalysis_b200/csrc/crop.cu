@@ -4,7 +4,9 @@
 // cuicuilco extract_subimages_rotate + images_asarray -> Pillow Image.transform(size, EXTENT, box,
 // NEAREST | BILINEAR), one Python iteration and one C call per window.
 //
-// Two kernels:
+// Tiled (window-minor) output -- what the detector uses -- is produced by ONE kernel, crop_tiled_kernel (below):
+// index tables in shared memory, batched gathers.  Row-major output (the drop-in host API) and patches too large
+// for shared-memory tables use the two-kernel path:
 //  1. crop_index_kernel: per window and axis, the 64-entry source-index table of Pillow's NEAREST
 //     resampler, reproduced bit-exactly: a = (hi - lo) / n in double, xo = lo + a * 0.5, then n
 //     *sequential* double additions (ImagingScaleAffine accumulates; the multiply form differs in the
