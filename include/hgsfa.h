@@ -42,8 +42,9 @@ enum { HGSFA_U8 = 0, HGSFA_F32 = 1, HGSFA_F64 = 2 };
 enum { HGSFA_ROWMAJOR = 0, HGSFA_TILED = 1 };
 #define HGSFA_TILE 128
 
-/* resampling filters, numerically equal to Pillow's Image.NEAREST / Image.BILINEAR */
-enum { HGSFA_NEAREST = 0, HGSFA_BILINEAR = 2 };
+/* resampling filters, numerically equal to Pillow's Image.NEAREST / Image.BILINEAR / Image.BICUBIC (the
+ * alternatives the reference lists for interpolation_formats, FaceDetectUpdated.py:125) */
+enum { HGSFA_NEAREST = 0, HGSFA_BILINEAR = 2, HGSFA_BICUBIC = 3 };
 
 typedef struct hgsfa_plan_s*  hgsfa_plan_t;
 typedef struct hgsfa_gauss_s* hgsfa_gauss_t;

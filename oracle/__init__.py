@@ -9,7 +9,7 @@ cascade controller.  Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_
 Pinning status:
 
 * grid / controller : restated line by line from ``face_analysis.py:575-669, 803-887`` (source in tree).
-* crop              : pinned against Pillow 12.2 ``Image.transform(EXTENT, NEAREST|BILINEAR)`` run live in
+* crop              : pinned against Pillow 12.2 ``Image.transform(EXTENT, NEAREST|BILINEAR|BICUBIC)`` run live in
                       the tests plus the fixtures under ``tests/golden/`` (Pillow's C core is what the
                       reference calls).
 * Gaussian head     : pinned against the 19 shipped ``SavedClassifiers/*.pckl`` parameter sets through

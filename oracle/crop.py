@@ -14,6 +14,12 @@ against Pillow 12.2 run live (``tests/test_oracle_crop.py``) and the fixtures in
 * BILINEAR (generic affine path): ``xin = a * (c + 0.5) + x0`` (multiply form); reject if outside
   ``[0, size)``; shift by -0.5; floor; lerp with edge-clamped neighbours; mode 'L' truncates.
 
+* BICUBIC (generic affine path, ``bicubic_filter8``): same source coordinate; reject if outside ``[0, size)``;
+  shift by -0.5; floor; 4 x 4 neighbourhood starting one pixel up-left, columns clamped to the image, a row
+  outside the image repeats the previous row's value (the first row is clamped); cubic
+  ``p1 + d (p2 + d (p3 + d p4))`` with ``p1 = v2, p2 = -v1 + v3, p3 = 2 (v1 - v2) + v3 - v4,
+  p4 = -v1 + v2 - v3 + v4``; clipped to [0, 255]; mode 'L' truncates.  PINNED against Pillow 12.2 live.
+
 angle != 0: cuicuilco crops a larger region, rotates it with ``rotate_improved(BICUBIC)`` and re-crops;
 that source is not available -- PARITY UNPINNED.  The oracle defines the rotated window as ONE affine
 NEAREST/BILINEAR resampling about the box centre (same sampling-point convention as above, multiply
@@ -84,6 +90,50 @@ def extent_bilinear(img, box, out_size=(64, 64)):
     return v.astype(np.uint8) if img.dtype == np.uint8 else v     # 'L': truncation
 
 
+def _cubic(v1, v2, v3, v4, d):
+    p1 = v2
+    p2 = -v1 + v3
+    p3 = 2 * (v1 - v2) + v3 - v4
+    p4 = -v1 + v2 - v3 + v4
+    return p1 + d * (p2 + d * (p3 + d * p4))
+
+
+def _bicubic_sample(img, xin, yin):
+    """Pillow's ``bicubic_filter8`` at continuous source coordinates (arrays of equal shape) -> uint8."""
+    H, W = img.shape
+    valid = (xin >= 0.0) & (xin < W) & (yin >= 0.0) & (yin < H)
+    xs = xin - 0.5
+    ys = yin - 0.5
+    xf = np.floor(xs)
+    yf = np.floor(ys)
+    dx = xs - xf
+    dy = ys - yf
+    x = xf.astype(np.int64) - 1
+    y = yf.astype(np.int64) - 1
+    f = img.astype(np.float64)
+    xc = [np.clip(x + k, 0, W - 1) for k in range(4)]
+    rows = []
+    for k in range(4):
+        yy = np.clip(y, 0, H - 1) if k == 0 else y + k
+        inside = np.ones_like(valid) if k == 0 else (yy >= 0) & (yy < H)
+        yr = np.clip(yy, 0, H - 1)
+        v = _cubic(f[yr, xc[0]], f[yr, xc[1]], f[yr, xc[2]], f[yr, xc[3]], dx)
+        rows.append(v if k == 0 else np.where(inside, v, rows[k - 1]))
+    r = _cubic(rows[0], rows[1], rows[2], rows[3], dy)
+    out = np.where(r <= 0.0, 0.0, np.where(r >= 255.0, 255.0, np.trunc(r)))
+    return np.where(valid, out, 0.0).astype(np.uint8)
+
+
+def extent_bicubic(img, box, out_size=(64, 64)):
+    ow, oh = out_size
+    ax = (np.float64(box[2]) - np.float64(box[0])) / ow
+    ay = (np.float64(box[3]) - np.float64(box[1])) / oh
+    xin = ax * (np.arange(ow) + 0.5) + np.float64(box[0])
+    yin = ay * (np.arange(oh) + 0.5) + np.float64(box[1])
+    X, Y = np.meshgrid(xin, yin)
+    return _bicubic_sample(img, X, Y)
+
+
 def rotated_sample_points(box, angle_deg, out_size=(64, 64)):
     """Continuous source coordinates of every output pixel for a window rotated by ``angle_deg``
     (the ``delta_ang`` handed to ``extract_subimages_rotate``, i.e. ``-curr_angle``) about its centre."""
@@ -101,9 +151,11 @@ def rotated_sample_points(box, angle_deg, out_size=(64, 64)):
     return cx + (U * c - V * s), cy + (U * s + V * c)
 
 
-def extent_rotated(img, box, angle_deg, out_size=(64, 64), bilinear=False):
+def extent_rotated(img, box, angle_deg, out_size=(64, 64), bilinear=False, bicubic=False):
     X, Y = rotated_sample_points(box, angle_deg, out_size)
     H, W = img.shape
+    if bicubic:
+        return _bicubic_sample(img, X, Y)
     if bilinear:
         v, _ = _bilinear_sample(img, X, Y)
         return v.astype(np.uint8) if img.dtype == np.uint8 else v
@@ -115,7 +167,7 @@ def extent_rotated(img, box, angle_deg, out_size=(64, 64), bilinear=False):
     return out.astype(img.dtype)
 
 
-NEAREST, BILINEAR = 0, 2   # Pillow's Image.NEAREST / Image.BILINEAR values
+NEAREST, BILINEAR, BICUBIC = 0, 2, 3   # Pillow's Image.NEAREST / Image.BILINEAR / Image.BICUBIC values
 
 
 def extract_subimages(img, coords, angles=None, out_size=(64, 64), interpolation=NEAREST):
@@ -131,10 +183,12 @@ def extract_subimages(img, coords, angles=None, out_size=(64, 64), interpolation
     for k in range(n):
         ang = 0.0 if angles is None else float(angles[k])
         if ang == 0.0:
-            p = extent_bilinear(img, coords[k], out_size) if interpolation == BILINEAR \
+            p = extent_bicubic(img, coords[k], out_size) if interpolation == BICUBIC \
+                else extent_bilinear(img, coords[k], out_size) if interpolation == BILINEAR \
                 else extent_nearest(img, coords[k], out_size)
         else:
-            p = extent_rotated(img, coords[k], -ang, out_size, bilinear=(interpolation == BILINEAR))
+            p = extent_rotated(img, coords[k], -ang, out_size, bilinear=(interpolation == BILINEAR),
+                               bicubic=(interpolation == BICUBIC))
         out[k] = p.reshape(-1)
     return out
 

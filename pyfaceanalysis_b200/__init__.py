@@ -13,6 +13,6 @@ All compute goes through ``libhgsfa.so`` (``include/hgsfa.h``); there is no CPU 
 from .pickles import load_obj, loads as unpickle  # noqa: F401
 from .gpuflow import GpuFlow, GpuNode  # noqa: F401
 from .classifier import GpuGaussianClassifier  # noqa: F401
-from .crop import extract_subimages, load_network_subimages, NEAREST, BILINEAR  # noqa: F401
+from .crop import extract_subimages, load_network_subimages, NEAREST, BILINEAR, BICUBIC  # noqa: F401
 
 __version__ = "0.1.0"

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libhgsfa.so")
 U8, F32, F64 = 0, 1, 2
 ROWMAJOR, TILED = 0, 1
 TILE = 128
-NEAREST, BILINEAR = 0, 2
+NEAREST, BILINEAR, BICUBIC = 0, 2, 3
 
 _DTYPES = {np.dtype(np.uint8): U8, np.dtype(np.float32): F32, np.dtype(np.float64): F64}
 

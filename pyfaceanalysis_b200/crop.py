@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 
-NEAREST, BILINEAR = _lib.NEAREST, _lib.BILINEAR
+NEAREST, BILINEAR, BICUBIC = _lib.NEAREST, _lib.BILINEAR, _lib.BICUBIC
 
 
 def _image_array(image):

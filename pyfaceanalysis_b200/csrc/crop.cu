@@ -2,7 +2,7 @@
 //
 // Replaces load_network_subimages (reference face_analysis.py:775-800) ->
 // cuicuilco extract_subimages_rotate + images_asarray -> Pillow Image.transform(size, EXTENT, box,
-// NEAREST | BILINEAR), one Python iteration and one C call per window.
+// NEAREST | BILINEAR | BICUBIC), one Python iteration and one C call per window.
 //
 // Tiled (window-minor) output -- what the detector uses -- is produced by ONE kernel, crop_tiled_kernel (below):
 // index tables in shared memory, batched gathers.  Row-major output (the drop-in host API) and patches too large
@@ -16,7 +16,7 @@
 //     image row (the image is L2-resident); patches are transposed through shared memory and
 //     written window-minor ("TILED") so that the flow kernels read them with 512-byte warp accesses,
 //     or written row-major for the drop-in host API.
-// Rotated windows (angle != 0) and BILINEAR take the generic per-pixel affine path in the same kernel.
+// Rotated windows (angle != 0), BILINEAR and BICUBIC take the generic per-pixel affine path in the same kernel.
 #include "common.cuh"
 
 namespace hgsfa {
@@ -77,6 +77,42 @@ __device__ __forceinline__ double bilinear_at(const uint8_t* __restrict__ img, i
   return __dadd_rn(v1, __dmul_rn(__dsub_rn(v2, v1), dy));
 }
 
+// Pillow bicubic_filter8 (Geometry.c), pinned against Pillow 12.2 (tests/test_oracle_crop.py): reject outside
+// [0, size); shift by -0.5; floor; 4 x 4 neighbourhood starting one pixel up-left with clamped columns; rows
+// outside the image repeat the previous row's value; clip to [0, 255]; mode 'L' truncates.
+__device__ __forceinline__ double bicubic_poly(double v1, double v2, double v3, double v4, double d) {
+  const double p1 = v2;
+  const double p2 = __dadd_rn(-v1, v3);
+  const double p3 = __dsub_rn(__dadd_rn(__dmul_rn(2.0, __dsub_rn(v1, v2)), v3), v4);
+  const double p4 = __dadd_rn(__dsub_rn(__dadd_rn(-v1, v2), v3), v4);
+  return __dadd_rn(p1, __dmul_rn(d, __dadd_rn(p2, __dmul_rn(d, __dadd_rn(p3, __dmul_rn(d, p4))))));
+}
+__device__ __forceinline__ uint8_t bicubic_at(const uint8_t* __restrict__ img, int W, int H, double xin, double yin) {
+  if (!(xin >= 0.0 && xin < double(W) && yin >= 0.0 && yin < double(H))) return 0;
+  const double xs = __dsub_rn(xin, 0.5), ys = __dsub_rn(yin, 0.5);
+  const double xf = floor(xs), yf = floor(ys);
+  const double dx = __dsub_rn(xs, xf), dy = __dsub_rn(ys, yf);
+  const int x = int(xf) - 1, y = int(yf) - 1;
+  int xc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) xc[k] = min(max(x + k, 0), W - 1);
+  double v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int yy = (k == 0) ? min(max(y, 0), H - 1) : y + k;
+    if (k == 0 || (yy >= 0 && yy < H)) {
+      const uint8_t* row = img + size_t(yy) * W;
+      v[k] = bicubic_poly(double(row[xc[0]]), double(row[xc[1]]), double(row[xc[2]]), double(row[xc[3]]), dx);
+    } else {
+      v[k] = v[k - 1];
+    }
+  }
+  const double r = bicubic_poly(v[0], v[1], v[2], v[3], dy);
+  if (r <= 0.0) return 0;
+  if (r >= 255.0) return 255;
+  return uint8_t(r);
+}
+
 // generic sample of output pixel (c, r) of window `box` rotated by delta_ang = -angle about its centre
 __device__ __forceinline__ uint8_t sample_generic(const uint8_t* __restrict__ img, int W, int H, const double* box,
                                                   double cs, double sn, bool rotated, int ow, int oh, int c, int r,
@@ -94,6 +130,7 @@ __device__ __forceinline__ uint8_t sample_generic(const uint8_t* __restrict__ im
     X = __dadd_rn(__dmul_rn(ax, double(c) + 0.5), x0);
     Y = __dadd_rn(__dmul_rn(ay, double(r) + 0.5), y0);
   }
+  if (filter == HGSFA_BICUBIC) return bicubic_at(img, W, H, X, Y);
   if (filter == HGSFA_BILINEAR) {
     bool valid;
     const double v = bilinear_at(img, W, H, X, Y, &valid);
@@ -402,8 +439,8 @@ int crop_launch(const uint8_t* d_img, int H, int W, ImageTable tab, const double
                 int64_t n, int ow, int oh, int filter, void* d_out, int out_dtype, int out_layout, void* stream) {
   HG_CHECK(ow > 0 && oh > 0, "hgsfa_crop_extent: bad patch size ow=%d oh=%d", ow, oh);
   HG_CHECK(ow <= 1024 && oh <= 1024, "hgsfa_crop_extent: patch size %dx%d too large", ow, oh);
-  HG_CHECK(filter == HGSFA_NEAREST || filter == HGSFA_BILINEAR,
-           "hgsfa_crop_extent: unsupported interpolation %d (NEAREST=0, BILINEAR=2)", filter);
+  HG_CHECK(filter == HGSFA_NEAREST || filter == HGSFA_BILINEAR || filter == HGSFA_BICUBIC,
+           "hgsfa_crop_extent: unsupported interpolation %d (NEAREST=0, BILINEAR=2, BICUBIC=3)", filter);
   HG_CHECK(n >= 0, "hgsfa_crop_extent: negative window count");
   HG_CHECK(out_layout == HGSFA_ROWMAJOR || (out_layout == HGSFA_TILED && out_dtype != HGSFA_F64),
            "hgsfa_crop_extent: tiled output must be u8 or f32");

@@ -43,8 +43,24 @@ def test_detection_grid_windows_vs_pillow(pipeline):
     assert np.array_equal(got, ref_all)
 
 
+def test_bicubic_bit_exact(crop_golden):
+    """BICUBIC (listed as an alternative by the reference, FaceDetectUpdated.py:125): device == oracle, which is
+    pinned against Pillow 12.2 in tests/test_oracle_crop.py; tiled and row-major outputs, overhanging boxes."""
+    from pyfaceanalysis_b200 import extract_subimages, BICUBIC
+    img, boxes = crop_golden["image"], crop_golden["boxes"]
+    got = extract_subimages(img, boxes, None, (64, 64), BICUBIC, np.uint8)
+    ref = ocrop.extract_subimages(img, boxes, None, (64, 64), BICUBIC).astype(np.uint8)
+    assert np.array_equal(got, ref)
+    rng = np.random.default_rng(8)
+    small = rng.integers(0, 256, (37, 41), dtype=np.uint8)
+    b = np.array([[-5.5, -3.2, 30.1, 28.9], [10.0, 12.0, 60.0, 50.0], [0.0, 0.0, 41.0, 37.0], [39.5, 35.5, 44.0, 40.0]])
+    got = extract_subimages(small, b, None, (32, 24), BICUBIC, np.float64)
+    ref = ocrop.extract_subimages(small, b, None, (32, 24), BICUBIC)
+    assert np.array_equal(got, ref)
+
+
 def test_rotated_windows_match_oracle():
-    from pyfaceanalysis_b200 import extract_subimages, NEAREST, BILINEAR
+    from pyfaceanalysis_b200 import extract_subimages, NEAREST, BILINEAR, BICUBIC
     rng = np.random.default_rng(4)
     img = rng.integers(0, 256, (300, 400), dtype=np.uint8)
     n = 60
@@ -54,7 +70,7 @@ def test_rotated_windows_match_oracle():
     coords = np.stack([x0, y0, x0 + s - 1, y0 + s - 1], axis=1)
     angles = rng.uniform(-25, 25, n)
     angles[::5] = 0.0
-    for interp in (NEAREST, BILINEAR):
+    for interp in (NEAREST, BILINEAR, BICUBIC):
         got = extract_subimages(img, coords, angles, (64, 64), interp, np.uint8)
         ref = ocrop.extract_subimages(img, coords, angles, (64, 64), interp).astype(np.uint8)
         mism = np.mean(got != ref)

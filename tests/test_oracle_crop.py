@@ -31,6 +31,8 @@ def test_live_pillow_random_and_adversarial():
                               np.asarray(pim.transform((64, 64), Image.EXTENT, b, Image.NEAREST)))
         assert np.array_equal(ocrop.extent_bilinear(img, b),
                               np.asarray(pim.transform((64, 64), Image.EXTENT, b, Image.BILINEAR)))
+        assert np.array_equal(ocrop.extent_bicubic(img, b),
+                              np.asarray(pim.transform((64, 64), Image.EXTENT, b, Image.BICUBIC)))
 
 
 def test_multiply_form_would_be_wrong():
