@@ -7,6 +7,7 @@ Public surface (mirrors the reference's objects):
     GpuGaussianClassifier(clf_obj).regression(x, labels)  # classifiers[i].regression / .label
     load_network_subimages(...) / extract_subimages(...)  # face_analysis.load_network_subimages
     load_obj(base_dir, base_filename)                     # Cache.load_obj_from_cache
+    AttributeEstimator(net, age, race, gender).estimate   # estimate_age_race_gender on normalised crops
 
 All compute goes through ``libhgsfa.so`` (``include/hgsfa.h``); there is no CPU fallback.
 """
@@ -14,5 +15,6 @@ from .pickles import load_obj, loads as unpickle  # noqa: F401
 from .gpuflow import GpuFlow, GpuNode  # noqa: F401
 from .classifier import GpuGaussianClassifier  # noqa: F401
 from .crop import extract_subimages, load_network_subimages, NEAREST, BILINEAR, BICUBIC  # noqa: F401
+from .attributes import AttributeEstimator  # noqa: F401
 
 __version__ = "0.1.0"

@@ -191,3 +191,29 @@ def test_exotic_expansions_both_engines(engine, monkeypatch):
     y = g.execute(x)
     assert np.abs(y - ref).max() <= 1e-3 * max(1.0, np.abs(ref).std()), np.abs(y - ref).max()
     g.close()
+
+
+def test_attribute_estimator(u11l96_flow, classifiers):
+    """estimate_age_race_gender on normalised crops (face_analysis.py:1170-1306): one batched flow + the three REAL
+    shipped heads == the oracle evaluated the reference's way (per face)."""
+    from pyfaceanalysis_b200 import AttributeEstimator, GpuFlow, GpuGaussianClassifier, synthetic
+    from pyfaceanalysis_b200.attributes import map_real_gender_labels_to_strings, map_real_race_labels_to_strings
+    from oracle import gauss as ogauss
+    heads = {("Age" if "Age" in c.name else "Race" if "Race" in c.name else "Gender"): c
+             for c in classifiers if "Generalize" in c.name}
+    g = GpuFlow(u11l96_flow)
+    est = AttributeEstimator(g, *[GpuGaussianClassifier(heads[k]) for k in ("Age", "Race", "Gender")])
+    x = synthetic.synthetic_patches(37, (96, 96), 77)
+    age, age_std, race, gender, conf = est.estimate(x)
+    sl = g.execute(x)                                  # the heads are compared on the same (GPU) features
+    a_ref, s_ref = ogauss.regression(heads["Age"], sl[:, :4], heads["Age"].avg_labels, estimate_std=True)
+    assert np.allclose(age, a_ref, rtol=1e-9, atol=1e-9, equal_nan=True)
+    assert np.allclose(age_std, s_ref, rtol=1e-7, atol=1e-7, equal_nan=True)
+    r_ref = ogauss.regression(heads["Race"], sl[:, :5], heads["Race"].avg_labels)
+    g_ref = ogauss.regression(heads["Gender"], sl[:, :5], heads["Gender"].avg_labels)
+    ok = ~(np.isnan(r_ref) | np.isnan(g_ref))
+    assert np.allclose(conf["race_confidences"], np.abs(r_ref) / 2.0, rtol=1e-9, atol=1e-9, equal_nan=True)
+    assert [r for r, k in zip(race, ok) if k] == [r for r, k in zip(map_real_race_labels_to_strings(r_ref), ok) if k]
+    assert [r for r, k in zip(gender, ok) if k] == [r for r, k in zip(map_real_gender_labels_to_strings(g_ref), ok) if k]
+    assert len(est.estimate(np.zeros((0, 9216)))[0]) == 0
+    g.close()

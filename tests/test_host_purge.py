@@ -20,3 +20,15 @@ def test_purge_matches_oracle_loop():
         got = purge_detections(det)
         ref = np.array(ctl.purge([r for r in det])).reshape(-1, 10) if n else np.zeros((0, 10))
         assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_label_strings():
+    import pytest
+    from pyfaceanalysis_b200.attributes import map_real_gender_labels_to_strings, map_real_race_labels_to_strings
+    assert map_real_gender_labels_to_strings([-1.0, 0.0, 0.3, 1.0]) == ["Male", "Male", "Female", "Female"]
+    assert map_real_gender_labels_to_strings([-0.5, 0.5], long_text=False) == ["M", "F"]
+    assert map_real_race_labels_to_strings([-2.0, 0.0, 1.7]) == ["Black", "Black", "White"]
+    with pytest.raises(Exception, match="Unrecognized label"):
+        map_real_gender_labels_to_strings([1.5])
+    with pytest.raises(Exception, match="Unrecognized label"):
+        map_real_race_labels_to_strings([10.0])
