@@ -210,7 +210,7 @@ struct hgsfa_plan_s {
   std::vector<DevBuf> tc_bufs;       // tensor-core operand images (weights split into TF32 hi / lo, chunked)
   // measured on B200 (profiles/README_r01.md): launches of >= 128 Ki windows hide the wave tail of the
   // one-CTA-per-SM layer kernels; smaller chunks only pay when the batch itself is small
-  int64_t front_chunk = 262144, back_chunk = 262144;
+  int64_t front_chunk = 524288, back_chunk = 524288;
   int split = 0;                     // ops [0, split) run per front chunk, [split, n) per back chunk
   int64_t launches = 0;
   double last_ms = 0.0;
