@@ -6,14 +6,17 @@
 //     E = Ehi + Elo, W = Whi + Wlo (TF32 each);   Y ~= Ehi Whi + Ehi Wlo + Elo Whi   (FP32 accumulate in TMEM)
 // which keeps FP32-class accuracy (measured 5e-7 relative, tools/tc_probe.cu) at ~4x the FFMA2 rate.
 //
-// Roles inside a CTA (192 threads):
+// Roles inside a CTA (320 threads):
 //   warps 0-3  expansion: thread = window.  A thread evaluates the expansion terms of ITS window from the
 //              staged receptive field (conflict-free LDS: consecutive lanes = consecutive windows), splits
 //              every value into TF32 hi/lo and writes them to ITS tensor-memory lane (tcgen05.st 32x32b):
-//              the A operand never touches shared memory.  Later the same threads drain the accumulators
-//              (tcgen05.ld), add the bias, clip and store the window-minor output (coalesced).
-//   warp 4     MMA issue: one elected lane, operands in uniform registers, 3 MMAs per 8 terms.
-//   warp 5     producer: cp.async.bulk of receptive-field runs (+ x_mean | b) and of the weight chunks.
+//              the A operand never touches shared memory.
+//   warps 4-7  epilogue: thread = window again (same lane quarters).  Drain the accumulators (tcgen05.ld), add the
+//              bias, clip and store the window-minor output (coalesced) while the expansion warps are already on
+//              the next node: an in-order warp that also had to wait for its own MMAs was the bottleneck
+//              (35.7 -> 34.4 ms per step; HGSFA_TC_EPI=0 keeps the epilogue on the expansion warps).
+//   warp 8     MMA issue: one elected lane, operands in uniform registers, 3 MMAs per 8 terms.
+//   warp 9     producer: cp.async.bulk of receptive-field runs (+ x_mean | b) and of the weight chunks.
 // Loop order node -> term chunk (32 terms) -> tile: a weight chunk (hi and lo image, canonical K-major
 // no-swizzle core matrices, prepared on the host) is streamed ONCE per node through a small ring and
 // shared by the twc tiles of the CTA; the accumulators of all twc tiles stay live in tensor memory.
@@ -28,7 +31,13 @@ namespace hgsfa {
 #define HGSFA_TC_CK 32
 #endif
 constexpr int TC_CK = HGSFA_TC_CK;   // terms per chunk (A stage = TC_CK hi + TC_CK lo columns)
-constexpr int TC_THREADS = 192;
+#ifndef HGSFA_TC_EPI
+#define HGSFA_TC_EPI 1
+#endif
+// HGSFA_TC_EPI = 1: four dedicated epilogue warps (4-7) drain the accumulators; 0: the expansion warps do it
+constexpr int TC_EPI = HGSFA_TC_EPI;
+constexpr int TC_MMA_WARP = TC_EPI ? 8 : 4, TC_PROD_WARP = TC_MMA_WARP + 1;
+constexpr int TC_THREADS = (TC_PROD_WARP + 1) * 32;
 constexpr int TC_MAX_TW = 8;
 
 struct TcOpDev {
@@ -300,7 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tbase = *tmem_slot;
   const uint32_t a_col0 = uint32_t(nd * op.twc * op.Npad16);          // A stages follow the accumulator sets
 
-  if (warp == 5) {
+  if (warp == TC_PROD_WARP) {
     // ================================ producer ================================
     Ring rx(nstx), rw(nw);
     for (int node = node_begin; node < node_end; ++node, rx.next()) {
@@ -342,7 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         __syncwarp();
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == TC_MMA_WARP) {
     // ================================ MMA issue ================================
     const bool leader = elect_one();
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
@@ -383,21 +392,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else {
-    // ================================ expansion + epilogue (thread = window) ================================
-    const uint32_t lane_base = tbase + (uint32_t(warp * 32) << 16);
+    // ================================ expansion / epilogue (thread = window) ================================
+    const int win = tid & (TILE - 1);
+    const uint32_t lane_base = tbase + (uint32_t((warp & 3) * 32) << 16);
     const Term16* terms = reinterpret_cast<const Term16*>(smem + op.sm_terms);
     const Seg* segs = reinterpret_cast<const Seg*>(smem + op.sm_segs);
     const int* chunk_seg = reinterpret_cast<const int*>(smem + op.sm_chunkseg);
-    float* bias_buf = reinterpret_cast<float*>(smem + op.sm_bias);   // [4 warps][2 sets][Npad16]
+    float* bias_buf = reinterpret_cast<float*>(smem + op.sm_bias);   // 8 slots of Npad16 floats
 
-    auto epilogue = [&](int node, int set, uint32_t par) {
+    auto epilogue = [&](int node, int set, uint32_t par, const float* bias) {
       const int nvalid = __ldg(op.n_valid + node);
       const int col0 = __ldg(op.out_col + node) + __ldg(op.col_off + node);
-      const float* bias = bias_buf + (warp * 2 + set) * op.Npad16;
       for (int t = 0; t < vt; ++t) {
         mbar_wait_tc(&bars[TCB_DFULL + set * TC_MAX_TW + t], par);
         tc_fence_after();
-        float* out = xout + (size_t(tile0 + t) * op.out_dim + col0) * TILE + tid;
+        float* out = xout + (size_t(tile0 + t) * op.out_dim + col0) * TILE + win;
         const float clo = op.clip_lo, chi = op.clip_hi;
         for (int n0 = 0; n0 < op.Npad16; n0 += 16, out += 16 * TILE) {
           uint32_t v[16];
@@ -430,20 +439,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     };
 
+    if (TC_EPI && warp >= 4) {
+      // ---- dedicated epilogue warps: bias slots are written by expansion warp 0 before the node's first A stage is
+      // published, i.e. before any MMA of the node and therefore before its DFULL
+      Ring rd(nd);
+      int slot = 0;
+      for (int node = node_begin; node < node_end; ++node, rd.next(), slot = (slot + 1) & 7)
+        epilogue(node, rd.idx, rd.par, bias_buf + slot * op.Npad16);
+    } else {
     Ring rx(nstx), ra(na), rd(nd);
-    int prev_set = 0;
+    int prev_set = 0, slot = 0, prev_slot = 0;
     uint32_t prev_par = 0u;
-    for (int node = node_begin; node < node_end; ++node, rx.next(), rd.next()) {
+    for (int node = node_begin; node < node_end; ++node, rx.next(), rd.next(), slot = (slot + 1) & 7) {
       const int sx = rx.idx;
       mbar_wait_tc(&bars[TCB_XFULL + sx], rx.par);
       const uint8_t* stage = smem + op.sm_x0 + size_t(sx) * op.sm_xstage_bytes;
       const float* head = reinterpret_cast<const float*>(stage + size_t(op.twc) * op.sm_raw_bytes);
       const float* mean = head;
       const int d_pad = (op.d_in + 3) & ~3;
-      // bias of this node, kept past the release of the stage (the epilogue may run one node later)
-      // (each warp keeps its own copy: no barrier between the four expansion warps)
+      // bias of this node, kept past the release of the stage (the epilogue runs later, possibly on other warps):
+      // with epilogue warps one shared ring of 8 slots written by warp 0 (the epilogue is at most nd + na nodes
+      // behind), otherwise a private copy per expansion warp (2 sets x 4 warps = the same 8 slots)
+      float* bias_dst = bias_buf + (TC_EPI ? slot : (warp * 2 + rd.idx)) * op.Npad16;
       __syncwarp();
-      for (int i = lane; i < op.Npad16; i += 32) bias_buf[(warp * 2 + rd.idx) * op.Npad16 + i] = head[d_pad + i];
+      if (!TC_EPI || warp == 0)
+        for (int i = lane; i < op.Npad16; i += 32) bias_dst[i] = head[d_pad + i];
       __syncwarp();
 
       for (int c = 0; c < n_chunks; ++c) {
@@ -459,7 +479,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int cnt = sg.kind, ngroups = (sg.k1 - sg.k0) >> 3;     // kind = number of real terms of the piece
             const uint32_t col = a_stage + uint32_t(sg.k0);
             if (sg.ibase >= 0 && (sg.op == OP_ID || sg.op == OP_ABSPOW)) {
-              const IN_T* xp = xs + size_t(sg.ibase) * TILE + tid;
+              const IN_T* xp = xs + size_t(sg.ibase) * TILE + win;
               const float* mp = mean + sg.ibase;
               if (sg.op == OP_ABSPOW) tc_seg_rows<IN_T, 2>(xp, mp, cnt, ngroups, sg.p, col);
               else if (sg.nomean) tc_seg_rows<IN_T, 0>(xp, mp, cnt, ngroups, 0.f, col);
@@ -467,7 +487,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               continue;
             }
             if (sg.op == OP_TRI) {
-              const IN_T* xr = xs + size_t(sg.ibase) * TILE + tid;
+              const IN_T* xr = xs + size_t(sg.ibase) * TILE + win;
               const float* mr = mean + sg.ibase;
               switch (int(sg.p)) {
 #define HG_TRI(N_) case N_: tc_seg_tri<IN_T, N_>(xr, mr, sg.nomean, cnt, col); break;
@@ -481,7 +501,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const Term16* tp = terms + sg.pad1;                           // pad1 = first entry of the term table
             const int2* to = reinterpret_cast<const int2*>(smem + op.sm_toff) + sg.pad1;
             const float2* tm2 = reinterpret_cast<const float2*>(head + d_pad + op.Npad16) + sg.pad1;   // (x_mean[i], x_mean[j])
-            const IN_T* xt = xs + tid;
+            const IN_T* xt = xs + win;
 #pragma unroll 1
             for (int g = 0; g < ngroups; ++g) {
               float v[8];
@@ -526,15 +546,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[TCB_XFREE + sx]);     // receptive field consumed
-      if (nd == 2) {
-        if (node > node_begin) epilogue(node - 1, prev_set, prev_par);
-        prev_set = rd.idx;
-        prev_par = rd.par;
-      } else {
-        epilogue(node, rd.idx, rd.par);
+      if (!TC_EPI) {
+        if (nd == 2) {
+          if (node > node_begin) epilogue(node - 1, prev_set, prev_par, bias_buf + (warp * 2 + prev_set) * op.Npad16);
+          prev_set = rd.idx;
+          prev_par = rd.par;
+        } else {
+          epilogue(node, rd.idx, rd.par, bias_buf + (warp * 2 + rd.idx) * op.Npad16);
+        }
       }
+      (void)prev_slot;
     }
-    if (nd == 2 && node_end > node_begin) epilogue(node_end - 1, prev_set, prev_par);
+    if (!TC_EPI && nd == 2 && node_end > node_begin)
+      epilogue(node_end - 1, prev_set, prev_par, bias_buf + (warp * 2 + prev_set) * op.Npad16);
+    }
   }
 
   tc_fence_before();

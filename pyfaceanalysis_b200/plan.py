@@ -692,9 +692,9 @@ def _decompose_tc(op):
     best = None
     forced = {k: int(_os.environ[e]) for k, e in (("twc", "HGSFA_TC_TWC"), ("nd", "HGSFA_TC_ND"), ("nstx", "HGSFA_TC_NSTX"),
                                                   ("na", "HGSFA_TC_NA"), ("nw", "HGSFA_TC_NW")) if e in _os.environ}
-    # single-chunk ops (K <= 32: per-item hand-overs dominate) do best with one A stage and three small CTAs per
-    # SM (measured on U11L_64 layer 0: 9.1 -> 8.3 ms); everything else with two A stages and two CTAs per SM
-    tiers = ([(128, 75 * 1024, (1,))] if n_chunks == 1 and not forced else []) + [(c, m, TC_NA_CHOICES) for c, m in TC_TIERS]
+    # (a 128-column / one-A-stage / three-CTA tier for single-chunk ops was worth 9.1 -> 8.3 ms on layer 0 before the
+    # epilogue moved to its own warps; with them two CTAs of 320 threads do better: 7.8 ms)
+    tiers = [(c, m, TC_NA_CHOICES) for c, m in TC_TIERS]
     for max_cols, max_smem, na_choices in tiers:
       if best is not None:
         break
