@@ -4,7 +4,9 @@
 //     Y[tile, node] = terms(X[tile, gather[node]] - x_mean[node]) @ W[node] + b[node]
 // but the contraction runs as 3xTF32 tcgen05.mma with M = the 128 windows of a tile:
 //     E = Ehi + Elo, W = Whi + Wlo (TF32 each);   Y ~= Ehi Whi + Ehi Wlo + Elo Whi   (FP32 accumulate in TMEM)
-// which keeps FP32-class accuracy (measured 5e-7 relative, tools/tc_probe.cu) at ~4x the FFMA2 rate.
+// which keeps near-FP32 accuracy (5e-7 relative per contraction, tools/tc_probe.cu; 1.7e-4 x std end to end) and
+// takes the contraction off the FMA pipe: ~9 ms of tensor-pipe time per 1 Mi windows of U11L_64, so a step is bound
+// by the expansion code (34 ms against 61 ms for the FFMA2 kernel).
 //
 // Roles inside a CTA (320 threads):
 //   warps 0-3  expansion: thread = window.  A thread evaluates the expansion terms of ITS window from the
@@ -127,9 +129,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
-}
-__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -448,7 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         epilogue(node, rd.idx, rd.par, bias_buf + slot * op.Npad16);
     } else {
     Ring rx(nstx), ra(na), rd(nd);
-    int prev_set = 0, slot = 0, prev_slot = 0;
+    int prev_set = 0, slot = 0;
     uint32_t prev_par = 0u;
     for (int node = node_begin; node < node_end; ++node, rx.next(), rd.next(), slot = (slot + 1) & 7) {
       const int sx = rx.idx;
@@ -555,7 +554,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           epilogue(node, rd.idx, rd.par, bias_buf + (warp * 2 + rd.idx) * op.Npad16);
         }
       }
-      (void)prev_slot;
     }
     if (!TC_EPI && nd == 2 && node_end > node_begin)
       epilogue(node_end - 1, prev_set, prev_par, bias_buf + (warp * 2 + prev_set) * op.Npad16);
