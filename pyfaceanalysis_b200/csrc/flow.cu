@@ -448,7 +448,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
         const int cols = t.nd * t.twc * t.Npad16 + t.na * 2 * TC_CK;
         t.tmem_cols = 32;
         while (t.tmem_cols < cols) t.tmem_cols *= 2;
-        if (!(t.nd == 1 || t.nd == 2) || !(t.nstx == 1 || t.nstx == 2) || t.nw < 2 || t.nw > 4 || !(t.na == 1 || t.na == 2 || t.na == 4) ||
+        if (!(t.nd == 1 || t.nd == 2) || !(t.nstx == 1 || t.nstx == 2) || t.nw < 2 || t.nw > 4 || !(t.na >= 1 && t.na <= 4) ||
             t.twc > TC_MAX_TW || t.Npad16 > 128 || cols > 512 || n_max > dp.Npad)
           return plan_fail(pl, "op %lld: bad tensor-core configuration (twc=%d Npad16=%d nd=%d nstx=%d nw=%d na=%d cols=%d)",
                            (long long)o, t.twc, t.Npad16, t.nd, t.nstx, t.nw, t.na, cols);
