@@ -630,6 +630,7 @@ ENGINE = _os.environ.get("HGSFA_ENGINE", "auto")
 TC_MIN_K = int(_os.environ.get("HGSFA_TC_MIN_K", "0"))
 TC_CK = int(_os.environ.get("HGSFA_TC_CK", "32"))          # terms per chunk (csrc/layer_tc.cuh, compile-time constant there)
 # two CTAs per SM (256 tensor-memory columns, 113 KB each): measured 56.8 vs 87.8 ms per 1M windows against one big CTA
+TC_L2_BPNS = float(_os.environ.get("HGSFA_TC_L2_BPNS", "30"))   # weight-chunk streaming rate assumed by the cost model
 TC_NA_CHOICES = tuple(int(v) for v in _os.environ.get("HGSFA_TC_NA_CHOICES", "2,4").split(","))
 TC_TIERS = [(int(a), int(b) * 1024) for a, b in
             (t.split(":") for t in _os.environ.get("HGSFA_TC_TIERS", "256:113,512:227").split(","))]   # (columns, KB) per CTA
@@ -712,7 +713,7 @@ def _decompose_tc(op):
                         smem = fixed + nstx * up(twc * op.d_in * TILE * 4 + head * 4) + nw * up(wstage)
                         if smem > SMEM_LIMIT or cols > max_cols or smem > max_smem:
                             continue
-                        t_w = n_chunks * wstage / twc / 10.0                          # L2 -> SM bytes at ~10 B/ns per SM
+                        t_w = n_chunks * wstage / twc / TC_L2_BPNS                    # L2 -> SM bytes per ns and SM
                         t = max(t_mma, t_w)
                         if nstx == 1:
                             t += (1500.0 + op.d_in * TILE * 4 * twc / 100.0) / twc    # exposed receptive-field load per node
