@@ -136,7 +136,9 @@ class ClockSampler(object):
         self.path = None
 
     def start(self):
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        # started before the warm-up (nvidia-smi needs up to a second to deliver its first sample on an 8-GPU box);
+        # stop(t0, t1) keeps the samples whose timestamp falls inside the timed region
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         fd, self.path = tempfile.mkstemp(suffix=".csv")
@@ -148,7 +150,16 @@ class ClockSampler(object):
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def has_output(self):
+        try:
+            return self.proc is None or os.path.getsize(self.path) > 0
+        except OSError:
+            return True
+
+    def stop(self, t0=None, t1=None):
+        """t0, t1: wall-clock (time.time()) bounds of the timed region; samples outside are dropped unless none
+        fall inside, in which case the samples taken under load since the warm-up are used and the window says so."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -157,7 +168,7 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        rows = []
         try:
             with open(self.path) as f:
                 for line in f:
@@ -165,20 +176,23 @@ class ClockSampler(object):
                     if len(c) < 9:
                         continue
                     try:
-                        sm.append(float(c[1]))
-                        smax.append(float(c[2]))
+                        ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                        rows.append((ts, float(c[1]), float(c[2]),
+                                     [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                               "sw_power_cap"), c[5:9]) if v.lower().startswith("active")]))
                     except ValueError:
                         continue
-                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                       c[5:9]):
-                        if v.lower().startswith("active"):
-                            reasons.add(name)
             os.unlink(self.path)
         except OSError:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
-                       samples=len(sm))
+        inside = [r for r in rows if t0 is None or (t0 - 0.05 <= r[0] <= t1 + 0.05)]
+        window = "timed region"
+        if not inside and rows:
+            inside = [r for r in rows if r[1] > 0.9 * max(x[1] for x in rows)] or rows     # under load since the warm-up
+            window = "warm-up + timed region (no nvidia-smi sample fell inside the timed region)"
+        if inside:
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=sorted({n for r in inside for n in r[3]}), samples=len(inside), window=window)
         return out
 
 
@@ -288,15 +302,21 @@ def main():
     def step():
         g.execute_torch(x_dev, out=y_dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize(dev)
+    # keep the GPU loaded (extra untimed steps) until nvidia-smi has delivered its first sample, 3 s at most
+    t_wait = time.time()
+    while not sampler.has_output() and time.time() - t_wait < 3.0:
+        step()
+        torch.cuda.synchronize(dev)
     g.profile(True)          # CUDA events around every layer launch of the timed steps (per-op device time)
     l0 = g.stats()["launches"]
-    sampler = ClockSampler(local_rank)
     barrier()
     torch.cuda.synchronize(dev)
-    sampler.start()
+    wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     per_step_kernel_ms = []
     e0.record(stream)
@@ -305,7 +325,7 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize(dev)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, time.time())
     ms_total = e0.elapsed_time(e1)
     launches = g.stats()["launches"] - l0
     kernel_ms_last = g.stats()["last_ms"]      # device time of the last step's launches (plan events)
@@ -364,7 +384,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
-                       "samples": clocks["samples"]},
+                       "samples": clocks["samples"], "window": clocks.get("window")},
             "roofline": _roofline(op_stats, args.steps, n, fl, kernel_ms_last, peaks, fp32_peak, fp32_src, tpw, tsrc, lshare),
         }
         if not args.no_cpu_baseline:
