@@ -32,3 +32,36 @@ def test_label_strings():
         map_real_gender_labels_to_strings([1.5])
     with pytest.raises(Exception, match="Unrecognized label"):
         map_real_race_labels_to_strings([10.0])
+
+
+def test_clock_sampler_window(tmp_path):
+    """bench.py's nvidia-smi parser: only samples inside the timed region count; none inside -> samples under load."""
+    import datetime
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t = 1_800_000_000.0
+
+    def line(dt, mhz, cap):
+        ts = datetime.datetime.fromtimestamp(t + dt).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return "%s, %d, 1965, 700.0, 0x4, Not Active, Not Active, Not Active, %s\n" % (ts, mhz, cap)
+
+    class Dead(object):
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            pass
+
+    for lines, expect in (([line(-1.0, 500, "Not Active"), line(0.1, 1900, "Active"), line(0.3, 1950, "Active"), line(2.0, 600, "Not Active")],
+                           (1925.0, 2, ["sw_power_cap"], "timed region")),
+                          ([line(-0.5, 1930, "Not Active"), line(-0.3, 300, "Not Active")], (1930.0, 1, [], None))):
+        path = tmp_path / "smi.csv"
+        path.write_text("".join(lines))
+        s = bench.ClockSampler(0)
+        s.proc, s.path = Dead(), str(path)
+        out = s.stop(t, t + 0.5)
+        assert out["sm_mhz"] == expect[0] and out["samples"] == expect[1] and out["reasons"] == expect[2]
+        assert out["sm_max_mhz"] == 1965.0 and (expect[3] is None or out["window"] == expect[3])
