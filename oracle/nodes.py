@@ -86,6 +86,11 @@ def flownode_execute(node, x):
     return flow_execute(flow, x)
 
 
+# "scaled": x_app = lr_node(sfa_x[:, :J] * magn_n_sfa_x);  "unscaled": x_app = lr_node(sfa_x[:, :J]).
+# Tests flip this together with pyfaceanalysis_b200.plan.IGSFA_LR_INPUT; real pickles decide which one is right.
+IGSFA_LR_INPUT = __import__("os").environ.get("HGSFA_IGSFA_LR_INPUT", "scaled")
+
+
 def igsfa_execute(node, x):
     """cuicuilco iGSFANode (older pickles: IEVMLRecNode), SURVEY.md row a-11:
 
@@ -100,9 +105,13 @@ def igsfa_execute(node, x):
     e = execute(expn, xp) if expn is not None else xp
     s = execute(node.sfa_node, e)
     J = int(node.num_sfa_features_preserved)
-    s_n = s[:, :J] * np.asarray(_get(node, "magn_n_sfa_x", default=1.0), dtype=np.float64)
+    magn = np.asarray(_get(node, "magn_n_sfa_x", default=1.0), dtype=np.float64).reshape(-1)
+    s_n = s[:, :J] * (magn if magn.size == 1 else magn[:J])          # n_sfa_x = sfa_x * magn_n_sfa_x, first J kept
     if _get(node, "reconstruct_with_sfa", default=True) and J > 0:
-        x_app = execute(node.lr_node, s_n)
+        # UNPINNED detail (cuicuilco source unavailable): is the linear reconstruction fed with the rescaled
+        # slow features n_sfa_x (our reading: lr_node is trained on them) or with the raw sfa_node output?
+        # IGSFA_LR_INPUT selects; the product's lowering has the same switch (plan.IGSFA_LR_INPUT).
+        x_app = execute(node.lr_node, s_n if IGSFA_LR_INPUT == "scaled" else s[:, :J])
     else:
         x_app = 0.0
     pca = _get(node, "pca_node")

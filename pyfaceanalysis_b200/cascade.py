@@ -205,6 +205,12 @@ class FaceDetector(object):
         """images: list of 2-D uint8 arrays (the reference's mode-'L' image, already prescaled).
         Returns a list (one entry per image) of (M,10) float64 detection arrays after the purge; with
         ``return_trace`` also a dict with the per-stage window counts and the un-purged detections."""
+        # the detector's device becomes current for the call: torch allocations, the stream looked up below and
+        # every kernel launch then agree, whatever device the calling thread had selected
+        with self.torch.cuda.device(self.dev):
+            return self._detect(images, smallest_face, return_trace)
+
+    def _detect(self, images, smallest_face, return_trace):
         torch = self.torch
         lib = _lib.load()
         dev = self.dev

@@ -194,6 +194,8 @@ extern "C" int hgsfa_cascade_update_device(int type, double* d_coords, double* d
   p.min_scale_radio = params12[5]; p.max_scale_radio = params12[6];
   p.tolerance_posxy = params12[7]; p.tolerance_scale = params12[8]; p.tolerance_angle = params12[9];
   p.desired_sampling = params12[10]; p.cut_off_face = params12[11];
+  PtrDeviceGuard guard(d_coords);
+  HG_CHECK(guard.ok, "hgsfa_cascade_update: cannot select device %d", guard.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cascade_update_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(type, d_coords, d_angles, d_reg_out, d_orig_coords,
                                                                    d_orig_angles, d_orig_index, d_patch_wh, n, p, d_keep,
@@ -206,6 +208,8 @@ extern "C" int hgsfa_compact_index_device(const uint8_t* d_keep, int64_t n, int3
                                           int32_t* d_scratch, int64_t scratch_ints, void* stream) {
   HG_CHECK(n >= 0 && n < (int64_t(1) << 31), "hgsfa_compact_index: count %lld out of range", (long long)n);
   HG_CHECK(d_count, "hgsfa_compact_index: null count");
+  PtrDeviceGuard guard(d_count);
+  HG_CHECK(guard.ok, "hgsfa_compact_index: cannot select device %d", guard.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n == 0) {
     HG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
@@ -227,6 +231,8 @@ extern "C" int hgsfa_gather_rows_device(const void* d_src, void* d_dst, const in
            (long long)n_out, (long long)row_bytes);
   if (n_out == 0) return 0;
   HG_CHECK(d_src && d_dst && d_index, "hgsfa_gather_rows: null buffer");
+  PtrDeviceGuard guard(d_dst);
+  HG_CHECK(guard.ok, "hgsfa_gather_rows: cannot select device %d", guard.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   gather_rows_kernel<<<(unsigned)ceil_div(n_out * 32, 256), 256, 0, st>>>(static_cast<const uint8_t*>(d_src),
                                                                          static_cast<uint8_t*>(d_dst), d_index, n_out,

@@ -42,6 +42,27 @@ struct DeviceGuard {
   }
 };
 
+// Entry points that take raw device buffers and no handle run on the device that owns the buffer, whatever
+// device is current in the calling thread (a detector bound to cuda:k is driven from threads whose current
+// device is 0).  Falls back to the current device for pointers CUDA does not know.
+inline int device_of(const void* p) {
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (!p) return cur;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return cur;
+  }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : cur;
+}
+struct PtrDeviceGuard : DeviceGuard {
+  int device;
+  explicit PtrDeviceGuard(const void* p) : PtrDeviceGuard(device_of(p), 0) {}
+ private:
+  PtrDeviceGuard(int dev, int) : DeviceGuard(dev), device(dev) {}
+};
+
 // grow-only device buffer
 struct DevBuf {
   void* p = nullptr;

@@ -447,8 +447,9 @@ int crop_launch(const uint8_t* d_img, int H, int W, ImageTable tab, const double
   if (n == 0) return 0;
   HG_CHECK(d_boxes && d_out, "hgsfa_crop_extent: null buffer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int device = 0;
-  HG_CUDA(cudaGetDevice(&device));
+  PtrDeviceGuard guard(d_out);                     // the device that owns the output, not the thread's current one
+  HG_CHECK(guard.ok, "hgsfa_crop_extent: cannot select device %d", guard.device);
+  const int device = guard.device;
   CropScratch& sc = scratch_for(device);
   // tiled output with tables that fit in shared memory: one fused kernel; otherwise tables through global memory
   const size_t stage_bytes = (size_t(ow) * (TILE_W + 4) + 15) & ~size_t(15);
@@ -528,6 +529,8 @@ extern "C" int hgsfa_contrast_avg_std_device(float* d_patches_tiled, int64_t n, 
   HG_CHECK(n >= 0 && dim > 0, "hgsfa_contrast_avg_std: bad shape n=%lld dim=%lld", (long long)n, (long long)dim);
   if (n == 0) return 0;
   HG_CHECK(d_patches_tiled, "hgsfa_contrast_avg_std: null buffer");
+  PtrDeviceGuard guard(d_patches_tiled);
+  HG_CHECK(guard.ok, "hgsfa_contrast_avg_std: cannot select device %d", guard.device);
   contrast_avg_std_kernel<<<(unsigned)ceil_div(n, TILE_W), TILE_W, 0, static_cast<cudaStream_t>(stream)>>>(
       d_patches_tiled, n, dim, obj_avg, obj_std);
   HG_CUDA(cudaGetLastError());

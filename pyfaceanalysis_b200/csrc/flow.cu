@@ -679,6 +679,11 @@ extern "C" int hgsfa_plan_stats(hgsfa_plan_t pl, int64_t* launches, double* last
 
 extern "C" int hgsfa_plan_set_chunks(hgsfa_plan_t pl, int64_t front_chunk, int64_t back_chunk) {
   HG_CHECK(pl, "hgsfa_plan_set_chunks: null plan");
+  // tile indices ride on gridDim.y (layout kernels) and gridDim.x / twc (layer kernels): a chunk holds at most
+  // 65 532 tiles (8.39 M windows); larger requests are clamped, the chunk loop covers the rest
+  const int64_t max_chunk = int64_t(65532) * TILE;
+  front_chunk = std::min(front_chunk, max_chunk);
+  back_chunk = std::min(back_chunk, max_chunk);
   if (front_chunk > 0) pl->front_chunk = ceil_div(front_chunk, 4 * TILE) * 4 * TILE;
   if (back_chunk > 0) pl->back_chunk = ceil_div(back_chunk, 4 * TILE) * 4 * TILE;
   if (pl->back_chunk < pl->front_chunk) pl->back_chunk = pl->front_chunk;
@@ -692,7 +697,18 @@ extern "C" int hgsfa_tile_windows_device(const void* d_src, int dtype, int64_t n
   HG_CHECK(n >= 0 && dim > 0 && ld >= dim, "hgsfa_tile_windows_device: bad shape n=%lld dim=%lld ld=%lld",
            (long long)n, (long long)dim, (long long)ld);
   if (n == 0) return 0;
+  PtrDeviceGuard guard(d_dst);
+  HG_CHECK(guard.ok, "hgsfa_tile_windows_device: cannot select device %d", guard.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t max_piece = int64_t(65532) * TILE;       // gridDim.y carries the tile index
+  if (n > max_piece) {
+    const size_t sel = dtype_size(dtype), del = dtype_size(dst_dtype);
+    for (int64_t w0 = 0; w0 < n; w0 += max_piece)
+      if (hgsfa_tile_windows_device(static_cast<const uint8_t*>(d_src) + size_t(w0) * ld * sel, dtype, std::min(max_piece, n - w0), dim,
+                                    ld, static_cast<uint8_t*>(d_dst) + size_t(w0) * dim * del, dst_dtype, stream))
+        return 1;
+    return 0;
+  }
   dim3 grid((unsigned)ceil_div(dim, 64), (unsigned)ceil_div(n, TILE));
   if (dtype == HGSFA_U8 && dst_dtype == HGSFA_U8 && ld % 16 == 0 && (reinterpret_cast<uintptr_t>(d_src) & 15) == 0) {
     dim3 g8((unsigned)ceil_div(dim, 128), (unsigned)ceil_div(n, TILE));

@@ -115,9 +115,12 @@ def terms_for(name, d):
         return _BASE[name](d)
     m = _EXPO_RE.match(name)
     if m:
-        p = float("0.%s%s" % (m.group(2), m.group(3))) if m.group(2) == "0" else None
-        if p is not None:
-            return (_abspow(p) if m.group(1) else _sgnpow(p))(d)
+        # cuicuilco names carry the exponent as "0Y" = 0.Y (unsigned_08expo = |x|^0.8); other forms are refused
+        if m.group(2) != "0":
+            raise KeyError("nonlinear_expansion function %r: exponent form %s%s is not 0Y (register it in "
+                           "pyfaceanalysis_b200/expansions.py)" % (name, m.group(2), m.group(3)))
+        p = int(m.group(3)) / 10.0
+        return (_abspow(p) if m.group(1) else _sgnpow(p))(d)
     m = _CLIP_RE.match(name)
     if m:
         p = float(m.group(1).replace("p", "."))

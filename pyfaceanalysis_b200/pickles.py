@@ -111,23 +111,47 @@ def canonical_module(module):
     return module
 
 
+# Exact (module, name) pairs a model pickle may resolve outside mdp / cuicuilco.  Anything else -- eval, exec,
+# getattr, __import__, os.system, numpy.testing helpers ... -- is refused: REDUCE on an arbitrary global is
+# arbitrary code execution.
+_SAFE_GLOBALS = {
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "scalar"),
+    ("numpy._core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "scalar"),
+    ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy", "float64"), ("numpy", "float32"), ("numpy", "int64"),
+    ("numpy", "int32"), ("numpy", "uint8"), ("numpy", "bool_"), ("numpy", "complex128"),
+    ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer"),
+    ("numpy.random", "__RandomState_ctor"), ("numpy.random.mtrand", "RandomState"),
+    ("copy_reg", "_reconstructor"), ("copyreg", "_reconstructor"),
+    ("__builtin__", "object"), ("__builtin__", "set"), ("__builtin__", "frozenset"), ("__builtin__", "slice"),
+    ("__builtin__", "complex"), ("__builtin__", "bytearray"), ("__builtin__", "tuple"), ("__builtin__", "list"),
+    ("__builtin__", "dict"), ("__builtin__", "long"), ("__builtin__", "int"), ("__builtin__", "float"),
+    ("__builtin__", "bool"), ("__builtin__", "str"), ("__builtin__", "unicode"), ("__builtin__", "range"),
+    ("__builtin__", "xrange"),
+    ("builtins", "object"), ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "slice"),
+    ("builtins", "complex"), ("builtins", "bytearray"), ("builtins", "tuple"), ("builtins", "list"),
+    ("builtins", "dict"), ("builtins", "int"), ("builtins", "float"), ("builtins", "bool"), ("builtins", "str"),
+    ("builtins", "bytes"), ("builtins", "range"),
+    ("collections", "OrderedDict"), ("collections", "defaultdict"),
+    ("_codecs", "encode"),      # how Python 3 writes the bytes of a numpy array under protocol 2 (synthetic pickles)
+}
+_PY2_BUILTIN_NAMES = {"long": "int", "unicode": "str", "xrange": "range"}
+
+
 class _StubUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        if module.startswith("numpy"):
-            module = module.replace("numpy.core", "numpy._core")
-            return super().find_class(module, name)
-        if module in ("__builtin__", "builtins", "copy_reg", "copyreg", "collections"):
-            module = {"__builtin__": "builtins", "copy_reg": "copyreg"}.get(module, module)
-            return super().find_class(module, name)
-        if (module, name) == ("_codecs", "encode"):
-            # how Python 3 writes the bytes of a numpy array under protocol 2 (synthetic pickles)
+        if (module, name) in _SAFE_GLOBALS:
+            if module.startswith("numpy.core"):
+                module = module.replace("numpy.core", "numpy._core")
+            elif module in ("__builtin__", "copy_reg"):
+                module = {"__builtin__": "builtins", "copy_reg": "copyreg"}[module]
+                name = _PY2_BUILTIN_NAMES.get(name, name)
             return super().find_class(module, name)
         module = canonical_module(module)
         top = module.split(".")[0]
         if top not in ("mdp", "cuicuilco", "bimdp"):
             raise pickle.UnpicklingError(
-                "refusing to materialise %s.%s: only mdp/cuicuilco/numpy globals are expected in a "
-                "PyFaceAnalysis model pickle" % (module, name))
+                "refusing to materialise %s.%s: only mdp / cuicuilco classes and an allow-list of numpy / builtin "
+                "constructors are expected in a PyFaceAnalysis model pickle" % (module, name))
         if module in _FUNCTION_MODULES and name[:1].islower() or (
                 module in _FUNCTION_MODULES and name in ("QT", "CT", "QE", "TE", "QN", "CN")):
             return FuncRef(module, name)

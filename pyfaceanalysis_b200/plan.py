@@ -189,13 +189,13 @@ class _Lowerer(object):
         return p
 
     # -- node kinds
-    def linear(self, node, final):
+    def linear(self, node, final, fold_mean=False):
         avg, W, b = _linear_params(node)
         d = len(self.cur) if self.pending is None else len(self.pending)
         if W.shape[0] != d:
             raise ValueError("%s: x has dimension %d, should be %d" % (_cls(node), d, W.shape[0]))
         if avg is not None:
-            if self.pending is None:
+            if self.pending is None and not fold_mean:
                 self._shift_current(avg)
             else:
                 b = b - avg @ W    # mean of the expanded vector: fold
@@ -232,7 +232,9 @@ class _Lowerer(object):
         if pre is not None:
             if _cls(pre) not in _LINEAR:
                 raise UnsupportedFlow("iGSFA pre_expansion_node of class %r" % _cls(pre))
-            self.linear(pre, final=False)
+            # the pre-expansion mean goes into that projection's bias: the shared input offset must stay x_mean,
+            # because the PCA / residual branch below reads the same x0 = x - x_mean rows
+            self.linear(pre, final=False, fold_mean=True)
             p_src = list(self.cur)
         expn = _get(node, "exp_node")
         if expn is not None:
@@ -271,6 +273,11 @@ class _Lowerer(object):
             _, B, b0 = _linear_params(node.lr_node)      # x_app = s_n @ B + b0
             if B.shape != (J, d):
                 raise ValueError("iGSFA lr_node: beta maps %s, expected (%d, %d)" % (B.shape, J, d))
+            if IGSFA_LR_INPUT == "unscaled":
+                # lr_node fed with the raw sfa_node output: x_app = (s_n / magn) @ B + b0 -- one row scaling of B
+                B = B / magn[:J, None]
+            elif IGSFA_LR_INPUT != "scaled":
+                raise ValueError("HGSFA_IGSFA_LR_INPUT must be 'scaled' or 'unscaled', not %r" % (IGSFA_LR_INPUT,))
             self.prog.alg_flops += 2 * J * d + d
         else:
             B, b0 = np.zeros((J, d)), np.zeros(d)
@@ -773,6 +780,10 @@ def _fuse_id_pow(segs):
 
 
 FOLD_BIAS = float(_os.environ.get("HGSFA_FOLD_BIAS", "1.5"))
+# which slow features feed an iGSFA node's linear reconstruction (cuicuilco source unavailable):
+# "scaled" = sfa_x[:, :J] * magn_n_sfa_x (default: lr_node is trained on the rescaled features), "unscaled" = sfa_x[:, :J].
+# oracle/nodes.py has the same switch; a real SavedNetworks pickle run against recorded reference outputs settles it.
+IGSFA_LR_INPUT = _os.environ.get("HGSFA_IGSFA_LR_INPUT", "scaled")
 FUSE_ID_POW = _os.environ.get("HGSFA_FUSE_ID_POW", "1") != "0"
 
 

@@ -40,6 +40,17 @@ def test_legacy_module_aliases():
 def test_foreign_globals_are_refused():
     with pytest.raises(pickle.UnpicklingError, match="refusing"):
         pickles.loads(pickle.dumps(os.getcwd, protocol=2))
+    # a REDUCE on any of these is arbitrary code execution: builtins and numpy are allow-listed by exact name only
+    for mod, name in (("__builtin__", "eval"), ("builtins", "exec"), ("__builtin__", "getattr"), ("builtins", "__import__"),
+                      ("os", "system"), ("posix", "system"), ("numpy.testing._private.utils", "runstring"),
+                      ("numpy", "load"), ("subprocess", "Popen")):
+        blob = b"\x80\x02c" + mod.encode() + b"\n" + name.encode() + b"\n."
+        with pytest.raises(pickle.UnpicklingError, match="refusing"):
+            pickles.loads(blob)
+    # what a real pickle does need still resolves (Python-2 names included)
+    blob = b"\x80\x02c__builtin__\nset\n]q\x00(K\x01K\x02e\x85Rq\x01."
+    assert pickles.loads(blob) == {1, 2}
+    assert pickles.loads(b"\x80\x02c__builtin__\nlong\n.") is int
 
 
 def test_load_obj_none_sentinel(tmp_path):

@@ -148,13 +148,20 @@ def test_expansion_tables_match_oracle_functions():
     x = rng.standard_normal((20, 9)) * 3
     for name in ["identity", "QT", "CT", "QE", "TE", "unsigned_08expo", "signed_08expo", "unsigned_06expo",
                  "signed_04expo", "unsigned_sqrt", "signed_sqrt", "abs", "pair_prod_adj1_ex", "pair_prod_adj3_ex",
-                 "s4QT", "s6u08ex", "s3CT", "clip_2"]:
+                 "s4QT", "s6u08ex", "s3CT", "clip_2",
+                 # every 0Y exponent the generic rule accepts, not only the hard-coded 08 / 06 / 04
+                 "unsigned_02expo", "signed_09expo", "unsigned_01expo", "signed_03expo", "unsigned_05expo",
+                 "signed_07expo", "s5_unsigned_09expo", "s5signed_02expo"]:
         t = ex.lower([name], 9)
         got = plan_interp._eval_terms(t, x)
         ref = oexp.resolve(name)(x)
         assert got.shape == ref.shape, name
         assert np.allclose(got, ref, rtol=1e-6, atol=1e-6), name
     assert ex.term_flops(ex.lower(["QT"], 5)) == 15 and ex.term_flops(ex.lower(["identity"], 5)) == 0
+    assert ex.terms_for("unsigned_02expo", 2)[0][3] == pytest.approx(0.2) and ex.terms_for("signed_09expo", 2)[0][3] == pytest.approx(0.9)
+    for bad in ("unsigned_12expo", "signed_80expo"):      # not the cuicuilco 0Y form: refuse instead of guessing
+        with pytest.raises(KeyError):
+            ex.terms_for(bad, 3)
 
 
 def test_tile_choice_and_segments():
@@ -199,3 +206,49 @@ def test_tensor_core_configuration(u11l_flow, monkeypatch):
     assert np.allclose(plan_interp.run_plan(spec, x), plan_interp.run_plan(spec_f, x), rtol=1e-9, atol=1e-9)
     blob = plan.serialize(spec)
     assert (struct.unpack_from("<q", blob, 64 + 5 * 8)[0] >> 16) & 0xff == 1        # engine flag of op 0
+
+
+def _igsfa_node(rng, d=9, k_pre=None, J=3, P=4, funcs=("identity", "unsigned_08expo")):
+    """A hand-made iGSFA node (random parameters) with every optional part present."""
+    pre = None
+    d_exp_in = d
+    if k_pre:
+        pre = _pca(d, k_pre, rng)              # pre_expansion_node with a NON-ZERO mean (ADVICE r1: plan.py:235)
+        d_exp_in = k_pre
+    D = ex.expanded_dim(list(funcs), d_exp_in)
+    sfa = _sfa(D, J + 2, rng)
+    lr = new_object("mdp.nodes", "LinearRegressionNode", beta=rng.standard_normal((J + 1, d)), with_bias=True,
+                    _input_dim=J, _output_dim=d)
+    pca = _pca(d, P, rng)
+    return new_object("cuicuilco.igsfa_node", "iGSFANode", x_mean=rng.standard_normal((1, d)) * 2,
+                      pre_expansion_node=pre, exp_node=_exp(d_exp_in, list(funcs)), sfa_node=sfa, lr_node=lr, pca_node=pca,
+                      magn_n_sfa_x=(0.5 + rng.random((1, J + 2))) * 3, num_sfa_features_preserved=J,
+                      reconstruct_with_sfa=True, _input_dim=d, _output_dim=J + P)
+
+
+@pytest.mark.parametrize("mode", ["auto", "fold", "two_pass"])
+def test_igsfa_pre_expansion_node_keeps_x_mean(mode):
+    """The pre-expansion PCA's mean must not leak into the shared input offset: the PCA / residual branch reads
+    x0 = x - x_mean, not x - x_mean - avg_pre."""
+    rng = np.random.default_rng(11)
+    nodes = [_igsfa_node(rng, d=9, k_pre=5) for _ in range(3)]
+    x = rng.standard_normal((50, 27)) * 3
+    spec = _agree([_layer(nodes)], x, mode)
+    assert np.allclose(spec.ops[0].in_offset, np.concatenate([n.x_mean for n in nodes]))
+
+
+@pytest.mark.parametrize("lr_input", ["scaled", "unscaled"])
+@pytest.mark.parametrize("mode", ["fold", "two_pass"])
+def test_igsfa_lr_input_switch(monkeypatch, mode, lr_input):
+    """Both readings of cuicuilco's iGSFA reconstruction (lr_node on the rescaled or on the raw slow features) are
+    lowered; oracle and compiler flip together, and the two readings really differ."""
+    rng = np.random.default_rng(12)
+    nodes = [_igsfa_node(rng, d=8) for _ in range(2)]
+    x = rng.standard_normal((40, 16)) * 3
+    ref_scaled = onodes.flow_execute([_layer(nodes)], x)
+    monkeypatch.setattr(onodes, "IGSFA_LR_INPUT", lr_input)
+    monkeypatch.setattr(plan, "IGSFA_LR_INPUT", lr_input)
+    _agree([_layer(nodes)], x, mode)
+    ref = onodes.flow_execute([_layer(nodes)], x)
+    assert (lr_input == "scaled") == bool(np.allclose(ref, ref_scaled))
+    assert np.allclose(ref[:, :3], ref_scaled[:, :3])       # the slow part is the same under both readings
