@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhgsfa.so")
+# HGSFA_LIB: a differently built libhgsfa.so (kernel experiments: tools/build_variant.py); default = the in-tree build
+LIB_PATH = os.environ.get("HGSFA_LIB") or os.path.join(HERE, "libhgsfa.so")
 
 U8, F32, F64 = 0, 1, 2
 ROWMAJOR, TILED = 0, 1

@@ -15,13 +15,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhgsfa.so")
-SOURCES = ["common.cu", "flow.cu", "crop.cu", "gauss.cu", "cascade.cu"]
+SOURCES = ["common.cu", "flow.cu", "front.cu", "crop.cu", "gauss.cu", "cascade.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2,-Wall",
     "-I", os.path.join(ROOT, "include"),
-] + (["-DHGSFA_TC_CK=" + os.environ["HGSFA_TC_CK"]] if "HGSFA_TC_CK" in os.environ else [])
+] + (["-DHGSFA_TC_CK=" + os.environ["HGSFA_TC_CK"]] if "HGSFA_TC_CK" in os.environ else []) \
+  + (["-DHGSFA_FRONT_DEV"] if os.environ.get("HGSFA_FRONT_DEV") else [])     # development: one front instantiation
 
 
 def nvcc_path():

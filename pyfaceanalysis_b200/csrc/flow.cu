@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "layer.cuh"
 #include "layer_tc.cuh"
+#include "front_api.h"
 
 namespace hgsfa {
 
@@ -208,6 +209,12 @@ struct hgsfa_plan_s {
   DevBuf params;                     // the whole blob: every plan array is an offset into it
   DevBuf tin, front[2], mid, back[2], stage_x[2], stage_y[2];
   std::vector<DevBuf> tc_bufs;       // tensor-core operand images (weights split into TF32 hi / lo, chunked)
+  // fused front (csrc/front_tc.cuh): layers 0-2 in one lane-resident kernel when the blob carries its section
+  bool front_ok = false;
+  FrontDev front_dev{};
+  int front_np1 = 0, front_np2 = 0, front_img_h = 0;
+  DevBuf fbuf;                       // third-layer output of a front chunk
+  double front_ms = 0.0;
   // measured on B200 (profiles/README_r01.md): launches of >= 128 Ki windows hide the wave tail of the
   // one-CTA-per-SM layer kernels; smaller chunks only pay when the batch itself is small
   int64_t front_chunk = 524288, back_chunk = 524288;
@@ -331,7 +338,10 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
   const uint8_t* dbase = static_cast<const uint8_t*>(pl->params.p);
   auto dev_ptr = [&](const void* host) { return dbase + (static_cast<const uint8_t*>(host) - base); };
 
-  Cursor cur{base + 64, base + nbytes};
+  const int64_t front_off = hdr[3], front_bytes = hdr[4];
+  if (front_off < 0 || front_bytes < 0 || (front_off > 0 && (front_off % 16 || front_off < 64 || front_off + front_bytes > (int64_t)nbytes)))
+    return plan_fail(pl, "fused-front section [%lld, +%lld) outside the blob", (long long)front_off, (long long)front_bytes);
+  Cursor cur{base + 64, base + (front_off > 0 ? size_t(front_off) : nbytes)};
   int64_t cur_dim = pl->input_dim;
   for (int64_t o = 0; o < n_ops && cur.ok; ++o) {
     const int64_t* oh = cur.take<int64_t>(16);
@@ -612,6 +622,64 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
   // back segment = trailing ops with few nodes: they need many windows per launch to fill 148 SMs
   pl->split = (int)pl->ops.size();
   while (pl->split > 0 && pl->ops[pl->split - 1].dev.n_nodes <= 8) pl->split--;
+  // ---- fused front section (pyfaceanalysis_b200/front.py): layers 0-2 in one kernel ----
+  {
+    const char* env = getenv("HGSFA_FRONT");
+    if (front_off > 0 && front_bytes > 0 && !(env && env[0] == '0') && pl->ops.size() >= 4 && pl->split >= 3) {
+      Cursor fc{base + front_off, base + front_off + front_bytes};
+      const uint8_t* fh_raw = fc.take<uint8_t>(8 + 16 * 8 + 12 * 8);
+      if (!fh_raw || std::memcmp(fh_raw, "HGSFAFR1", 8) != 0) return plan_fail(pl, "bad fused-front section");
+      int64_t fh[16];
+      double ff[12];
+      std::memcpy(fh, fh_raw + 8, sizeof(fh));
+      std::memcpy(ff, fh_raw + 8 + sizeof(fh), sizeof(ff));
+      FrontDev& f = pl->front_dev;
+      f.n_sub = (int)fh[0]; f.img_w = (int)fh[1]; pl->front_img_h = (int)fh[2];
+      pl->front_np1 = (int)fh[3]; pl->front_np2 = (int)fh[4];
+      f.nn0 = (int)fh[5]; f.nn1 = (int)fh[6]; f.nn2 = (int)fh[7];
+      const int nv0 = (int)fh[8], nv1 = (int)fh[9];
+      f.nv_out = (int)fh[10]; f.nch1 = (int)fh[11]; f.nch2 = (int)fh[12];
+      f.out_dim = (int)fh[13]; f.sub_bytes = (int)fh[14];
+      f.in_dim = (int)pl->input_dim;
+      f.s0 = float(ff[0]); f.s1 = float(ff[1]); f.s2 = float(ff[2]);
+      f.clo0 = float(ff[3]); f.clo1 = float(ff[4]); f.clo2 = float(ff[5]);
+      f.chi0 = float(ff[6]); f.chi1 = float(ff[7]); f.chi2 = float(ff[8]);
+      f.p0 = float(ff[9]); f.p1 = float(ff[10]); f.p2 = float(ff[11]);
+      const int np1 = pl->front_np1, np2 = pl->front_np2;
+      const bool fsane =
+          f.n_sub > 0 && f.n_sub % 2 == 0 && f.n_sub <= 65534 && f.img_w >= 16 && f.img_w % 16 == 0 && pl->front_img_h >= 8 &&
+          int64_t(f.img_w) * pl->front_img_h == pl->input_dim && fh[15] == FR_HEAD && f.nn0 == 16 && (f.nn1 == 16 || f.nn1 == 32) &&
+          (f.nn2 == 16 || f.nn2 == 32) && np1 >= 8 && np1 <= 16 && np2 >= 8 && np2 <= 32 && np1 % 8 == 0 && np2 % 8 == 0 &&
+          nv0 >= 1 && nv0 <= np1 && nv1 >= 1 && nv1 <= np2 && np2 <= f.nn1 && f.nv_out >= 1 && f.nv_out <= f.nn2 &&
+          f.nch1 == 4 * np1 / 32 && f.nch2 == 4 * np2 / 32 && f.out_dim == pl->ops[2].dev.out_dim &&
+          f.sub_bytes == 4 * (FR_HEAD + f.nn0 * 128) + 2 * f.nch1 * (FR_HEAD + f.nn1 * 128) + f.nch2 * (FR_HEAD + f.nn2 * 128) &&
+          (2 * np1 + 2 * np1) * 4 <= FR_HEAD && (4 * np2 + 32) * 4 <= FR_HEAD && pl->ops[0].dev.n_nodes == 4 * f.n_sub &&
+          pl->ops[1].dev.n_nodes == 2 * f.n_sub && pl->ops[2].dev.n_nodes == f.n_sub;
+      if (!fsane) return plan_fail(pl, "inconsistent fused-front header (n_sub=%d np=(%d, %d) nn=(%d, %d, %d))", f.n_sub, np1, np2, f.nn0, f.nn1, f.nn2);
+      const int32_t* pair_xy = fc.take<int32_t>(size_t(f.n_sub));          // n_sub / 2 pairs of (x, y)
+      const int32_t* l0_off = fc.take<int32_t>(size_t(f.n_sub) * 4);
+      const int32_t* out_col = fc.take<int32_t>(size_t(f.n_sub));
+      const uint8_t* wimg = fc.take<uint8_t>(size_t(f.n_sub) * f.sub_bytes);
+      if (!fc.ok) return plan_fail(pl, "truncated fused-front section");
+      for (int k = 0; k < f.n_sub; ++k) {
+        const int px = pair_xy[(k / 2) * 2], py = pair_xy[(k / 2) * 2 + 1];
+        bool good = px >= 0 && py >= 0 && px % 16 == 0 && px + 16 <= f.img_w && py + 8 <= pl->front_img_h && out_col[k] >= 0 &&
+                    out_col[k] + f.nv_out <= f.out_dim;
+        for (int i = 0; i < 4 && good; ++i) {
+          const int dy = l0_off[k * 4 + i] & 0xff, dx = l0_off[k * 4 + i] >> 8;
+          good = dy >= 0 && dy <= 4 && dx >= 0 && dx <= 12 && dx % 4 == 0;
+        }
+        if (!good) return plan_fail(pl, "fused front: subtree %d has an invalid pixel box or output column", k);
+      }
+      f.pair_xy = reinterpret_cast<const int2*>(dev_ptr(pair_xy));
+      f.l0_off = reinterpret_cast<const int*>(dev_ptr(l0_off));
+      f.out_col = reinterpret_cast<const int*>(dev_ptr(out_col));
+      f.wimg = dev_ptr(wimg);
+      if ((reinterpret_cast<uintptr_t>(f.wimg) & 15) != 0) return plan_fail(pl, "fused front: weight chunks are not 16-byte aligned");
+      if (front_set_attributes(np1, np2)) { std::string msg = last_error_ref(); return plan_fail(pl, "%s", msg.c_str()); }
+      pl->front_ok = true;
+    }
+  }
   bool ok = cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 2 && ok; ++i)
@@ -631,7 +699,7 @@ extern "C" int hgsfa_plan_destroy(hgsfa_plan_t pl) {
   DeviceGuard guard(pl->device);
   if (pl->stream) cudaStreamSynchronize(pl->stream);
   if (pl->copy_stream) cudaStreamSynchronize(pl->copy_stream);
-  pl->params.release(); pl->tin.release(); pl->mid.release();
+  pl->params.release(); pl->tin.release(); pl->mid.release(); pl->fbuf.release();
   for (auto& b : pl->tc_bufs) b.release();
   for (int i = 0; i < 2; ++i) {
     pl->front[i].release(); pl->back[i].release(); pl->stage_x[i].release(); pl->stage_y[i].release();
@@ -779,7 +847,7 @@ extern "C" int hgsfa_plan_op_stats(hgsfa_plan_t pl, int64_t capacity, double* ms
   pl->stamps.clear();
   for (size_t o = 0; o < pl->ops.size(); ++o) {
     if (ms) ms[o] = pl->op_ms[o];
-    if (engine) engine[o] = pl->ops[o].tc ? 1 : 0;
+    if (engine) engine[o] = (pl->front_ok && o < 3) ? 2 : (pl->ops[o].tc ? 1 : 0);   // 2: fused front (uint8 inputs), time booked on op 0
     if (alg_flops) alg_flops[o] = double(pl->ops[o].alg_flops);
     if (exe_flops) exe_flops[o] = double(pl->ops[o].exe_flops);
   }
@@ -815,13 +883,20 @@ extern "C" int hgsfa_plan_execute_device(hgsfa_plan_t pl, const void* d_x, int x
   if (split == n_ops) bc = fc;    // no back segment: nothing to accumulate across front chunks
   bc = ceil_div(bc, fc) * fc;
 
-  int64_t maxf_front = 0, maxf_back = 0;
-  for (int o = 0; o < split; ++o) maxf_front = std::max<int64_t>(maxf_front, pl->ops[o].dev.out_dim);
-  for (int o = split; o < n_ops; ++o) maxf_back = std::max<int64_t>(maxf_back, pl->ops[o].dev.out_dim);
   const bool in_u8 = (x_dtype == HGSFA_U8);
   const size_t in_el = in_u8 ? 1 : 4;
-  if (x_layout == HGSFA_ROWMAJOR && pl->tin.reserve(size_t(fc) * pl->input_dim * in_el)) return 1;
-  if (split > 0)
+  // fused front: layers 0-2 in one kernel for uint8 windows (the detector's and the benchmark's input); row-major
+  // windows are read in place through a tensor map when rows are 16-byte aligned, else tiled first
+  const bool use_front = pl->front_ok && in_u8 && split >= 3;
+  const bool front_direct = use_front && x_layout == HGSFA_ROWMAJOR && ld % 16 == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0 &&
+                            front_tensor_maps_available();
+  const int o_first = use_front ? 3 : 0;      // first op that runs as a per-layer launch
+  int64_t maxf_front = 0, maxf_back = 0;
+  for (int o = o_first; o < split; ++o) maxf_front = std::max<int64_t>(maxf_front, pl->ops[o].dev.out_dim);
+  for (int o = split; o < n_ops; ++o) maxf_back = std::max<int64_t>(maxf_back, pl->ops[o].dev.out_dim);
+  if (x_layout == HGSFA_ROWMAJOR && !front_direct && pl->tin.reserve(size_t(fc) * pl->input_dim * in_el)) return 1;
+  if (use_front && split > 3 && pl->fbuf.reserve(size_t(fc) * pl->ops[2].dev.out_dim * 4)) return 1;
+  if (split > o_first)
     for (int i = 0; i < 2; ++i)
       if (pl->front[i].reserve(size_t(fc) * maxf_front * 4)) return 1;
   const int64_t mid_dim = split > 0 ? pl->ops[split - 1].dev.out_dim : pl->input_dim;
@@ -853,6 +928,8 @@ extern "C" int hgsfa_plan_execute_device(hgsfa_plan_t pl, const void* d_x, int x
       const void* xin;
       if (x_layout == HGSFA_TILED) {
         xin = xb + size_t(f0 / TILE) * pl->input_dim * TILE * in_el;
+      } else if (front_direct) {
+        xin = xb + size_t(f0) * ld;
       } else {
         const void* src = xb + size_t(f0) * ld * dtype_size(x_dtype);
         if (hgsfa_tile_windows_device(src, x_dtype, fn, pl->input_dim, ld, pl->tin.p, in_u8 ? HGSFA_U8 : HGSFA_F32, st))
@@ -866,8 +943,22 @@ extern "C" int hgsfa_plan_execute_device(hgsfa_plan_t pl, const void* d_x, int x
         continue;
       }
       float* fout = (split < n_ops) ? static_cast<float*>(pl->mid.p) + size_t((f0 - b0) / TILE) * mid_dim * TILE
-                                    : static_cast<float*>(pl->front[(split - 1) & 1].p);
-      if (run_ops(pl, 0, split, xin, in_u8, fout, pl->front, f_tiles, st)) return 1;
+                                    : static_cast<float*>(pl->front[(split - 1 - o_first) & 1].p);
+      if (use_front) {
+        float* fdst = split > 3 ? static_cast<float*>(pl->fbuf.p) : fout;
+        hgsfa_plan_s::Stamp stamp{0, nullptr, nullptr};
+        if (pl->profile && cudaEventCreate(&stamp.e0) == cudaSuccess && cudaEventCreate(&stamp.e1) == cudaSuccess)
+          cudaEventRecord(stamp.e0, st);
+        if (front_launch(pl->front_dev, pl->front_np1, pl->front_np2, pl->front_img_h, pl->sm_count,
+                         front_direct ? FR_IN_ROWMAJOR : FR_IN_TILED, static_cast<const uint8_t*>(xin), ld, fn, fdst, st))
+          return 1;
+        pl->launches++;
+        if (pl->profile && stamp.e1) {
+          cudaEventRecord(stamp.e1, st);
+          pl->stamps.push_back(stamp);
+        }
+        if (split > 3 && run_ops(pl, 3, split, fdst, false, fout, pl->front, f_tiles, st)) return 1;
+      } else if (run_ops(pl, 0, split, xin, in_u8, fout, pl->front, f_tiles, st)) return 1;
       if (split == n_ops && untile(fout, mid_dim, f0, fn)) return 1;
       back_in = pl->mid.p;
     }

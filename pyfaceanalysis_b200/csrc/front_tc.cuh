@@ -1,0 +1,490 @@
+// Fused front of a thin fan-in-2 HiGSFA network: layers 0, 1 and 2 in ONE kernel, lane-resident (sm_100a).
+//
+// Replaces the first three per-layer launches of mdp.Flow.execute (FaceDetectUpdated.py:699): the 4x4-pixel
+// first-layer nodes, the horizontal joins and the vertical joins form 8x8-pixel subtrees (4 + 2 + 1 nodes) that
+// never interact, and a window's path through a subtree never leaves its thread:
+//
+//   thread = window = tensor-memory lane.  Level 0: the thread reads its 16 pixels from the staged pixel box,
+//   evaluates [x | |x - m|^p], splits every value into two FP16 pieces and writes them to ITS lane of an A stage
+//   (tcgen05.st).  The MMA warp contracts the tile's 128 lanes against the node's weights (tcgen05.mma kind::f16,
+//   M = 128, N = 16 / 32, K = 16; three products per K step: Ahi Whi + Ahi Wlo + Alo Whi, FP32 accumulation).
+//   Level 1 / 2: the SAME thread reads the two child accumulators of its lane (tcgen05.ld), applies the children's
+//   bias + saturation, expands, splits and writes the next A stage.  Only the third level's output is stored to
+//   HBM (window-minor tiles, coalesced).  No activation of layers 0 and 1 ever exists in shared or global memory.
+//
+// Why FP16 pieces and not 3xTF32: profiles/tc_probe2_r02.txt -- an M128 N16 K16 kind::f16 MMA issues every 7.4 ns,
+// the M128 N16 K8 kind::tf32 one every 19.3 ns (5x per unit of K); two FP16 pieces carry 22 mantissa bits, the
+// relative error of a contraction is 4e-7 (3xTF32: 5e-7).  Operands are range-checked on the host
+// (pyfaceanalysis_b200/front.py: pixels, clipped activations, weights rescaled by 2^t per level).
+//
+// CTA = 11 warps, one per SM (all 512 tensor-memory columns):
+//   warps 0-3 / 4-7  expansion of tile group 0 / 1 (two tiles of 128 windows share every weight chunk)
+//   warps 8 / 9      MMA issue for group 0 / 1 (one elected lane)
+//   warp 10          producer: pixel boxes (3-D tensor map over row-major windows, or bulk copies of window-minor
+//                    tiles) and weight chunks (cp.async.bulk) through mbarrier rings
+// Item order per subtree s (software-pipelined so that no item depends on the one issued just before it):
+//   L0a(s) L0b(s) L2(s-1) L0c(s) L0d(s) L1ab(s) STORE(s-1) L1cd(s)
+// Tensor-memory columns per group: 4 x 16 (level-0 accumulators) + 2 x 32 (level 1) + 32 (level 2) + 3 x 32 (A ring).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "front_api.h"
+#include "layer_tc.cuh"
+
+namespace hgsfa {
+
+constexpr int FR_NW = 6;                 // weight-ring stages
+constexpr int FR_NA = 3;                 // A-ring stages per group (32 columns each: 16 hi + 16 lo)
+constexpr int FR_NX = 2;                 // pixel-box stages per group
+constexpr int FR_WSTAGE = FR_HEAD + 32 * 128;
+constexpr int FR_XSTAGE = 16 * 8 * TILE;  // 16 x 8 pixel box of 128 windows
+constexpr int FR_THREADS = 11 * 32;
+#ifndef HGSFA_FR_SLEEP_MMA
+#define HGSFA_FR_SLEEP_MMA 64
+#endif
+#ifndef HGSFA_FR_SLEEP_PROD
+#define HGSFA_FR_SLEEP_PROD 256
+#endif
+#ifndef HGSFA_FR_LAZY_PUBLISH
+#define HGSFA_FR_LAZY_PUBLISH 0
+#endif
+constexpr bool FR_LAZY_PUBLISH = HGSFA_FR_LAZY_PUBLISH != 0;
+constexpr int FR_SLEEP_MMA = HGSFA_FR_SLEEP_MMA, FR_SLEEP_PROD = HGSFA_FR_SLEEP_PROD;   // ns between barrier tries of the service warps
+constexpr int FR_GCOLS = 256;            // tensor-memory columns per group
+constexpr int FR_COL_L0 = 0, FR_COL_L1 = 64, FR_COL_L2 = 128, FR_COL_A = 160;
+// barriers: WFULL[6] WFREE[6] then per group AFULL[3] AFREE[3] DFULL[7] XFULL[2] XFREE[2]
+enum { FRB_WFULL = 0, FRB_WFREE = FR_NW, FRB_G = 2 * FR_NW, FRB_AFULL = 0, FRB_AFREE = FR_NA, FRB_DFULL = 2 * FR_NA,
+       FRB_XFULL = 2 * FR_NA + 7, FRB_XFREE = 2 * FR_NA + 7 + FR_NX, FRB_GSTRIDE = 2 * FR_NA + 7 + 2 * FR_NX,
+       FRB_COUNT = 2 * FR_NW + 2 * FRB_GSTRIDE };
+constexpr int FR_SM_BARS = 0, FR_SM_TMEM = 512, FR_SM_BIAS = 1024;               // bias: 8 warps x 32 floats
+constexpr int FR_SM_W = 2048, FR_SM_X = FR_SM_W + FR_NW * FR_WSTAGE + 512;        // pixel stages are 1024-aligned (below)
+constexpr int FR_SMEM = ((FR_SM_X + 1023) & ~1023) + 2 * FR_NX * FR_XSTAGE + 1024;
+
+__device__ __forceinline__ bool fr_try(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  return ok != 0;
+}
+template <int SLEEP_NS = 0>
+__device__ __forceinline__ void fr_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait is meant to suspend the warp in hardware (alone it does, ~4 us per call: profiles/tc_probe2_r02.txt) but inside
+  // this kernel it returns within tens of ns (profiles/ncu_r02_front_lines.txt: 17 % of the executed instructions were
+  // re-tries), so the service warps (MMA issue, producer) sleep between tries instead of stealing issue slots from the
+  // expansion warps of their scheduler.  A protocol error traps instead of hanging the GPU.
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    if (fr_try(addr, parity)) return;
+    if (SLEEP_NS > 0) {
+      __nanosleep(SLEEP_NS);
+    } else {
+      if (fr_try(addr, parity)) return;
+      if (fr_try(addr, parity)) return;
+      if (fr_try(addr, parity)) return;
+    }
+  }
+  __trap();
+}
+__device__ __forceinline__ uint32_t fr_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+__device__ __forceinline__ void fr_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {      // NC columns, multiple of 8
+#pragma unroll
+  for (int c = 0; c < NC; c += 8) tmem_ld8(taddr + c, v + c);
+}
+// two FP32 values -> FP16 pair (first value in the low half = the lower K index)
+__device__ __forceinline__ uint32_t fr_pack(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void fr_split(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = fr_pack(a, b);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = fr_pack(a - hf.x, b - hf.y);
+}
+__device__ __forceinline__ void fr_tensor_load(void* dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- expansion of a join node (levels 1 and 2): the children's accumulators -> A chunks of 32 terms ----
+template <int NP>
+struct FrJoin {
+  // values of the 2 NP inputs after the children's bias and saturation
+  template <typename PUB>
+  static __device__ __forceinline__ void run(uint32_t acc0, uint32_t acc1, const float* head, float s, float clo, float chi,
+                                             float p, PUB&& publish) {
+    float y[2 * NP];
+    {
+      uint32_t r[2 * NP];
+      tmem_ld_cols<NP>(acc0, r);
+      tmem_ld_cols<NP>(acc1, r + NP);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < 2 * NP; k += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(head + k);
+        y[k + 0] = fminf(fmaxf(fmaf(__uint_as_float(r[k + 0]), s, b.x), clo), chi);
+        y[k + 1] = fminf(fmaxf(fmaf(__uint_as_float(r[k + 1]), s, b.y), clo), chi);
+        y[k + 2] = fminf(fmaxf(fmaf(__uint_as_float(r[k + 2]), s, b.z), clo), chi);
+        y[k + 3] = fminf(fmaxf(fmaf(__uint_as_float(r[k + 3]), s, b.w), clo), chi);
+      }
+    }
+    const float* mean = head + 2 * NP;
+    constexpr int NCH = 4 * NP / 32;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int q = 0; q < 16; q += 2) {          // four terms per step: one LDS.128 of means serves the power terms
+        const int t = 32 * c + 2 * q;            // multiple of 4
+        float v[4];
+        if (t < 2 * NP) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = y[t + e];
+        } else {
+          const float4 m = *reinterpret_cast<const float4*>(mean + (t - 2 * NP));
+          v[0] = abspow(y[t - 2 * NP + 0] - m.x, p);
+          v[1] = abspow(y[t - 2 * NP + 1] - m.y, p);
+          v[2] = abspow(y[t - 2 * NP + 2] - m.z, p);
+          v[3] = abspow(y[t - 2 * NP + 3] - m.w, p);
+        }
+        fr_split(v[0], v[1], hi[q], lo[q]);
+        fr_split(v[2], v[3], hi[q + 1], lo[q + 1]);
+      }
+      const uint32_t col = publish.acquire();      // also hands the previous chunk to the MMA warp: its stores had this
+      tmem_st16(col, hi);                          // chunk's arithmetic to complete behind
+      tmem_st16(col + 16, lo);
+      publish.release();
+    }
+  }
+};
+
+template <int NP1, int NP2, int IN_MODE>
+__global__ void __launch_bounds__(FR_THREADS, 1)
+    front_kernel(const FrontDev fd, const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ xin,
+                 float* __restrict__ xout, int64_t ntiles) {
+  extern __shared__ __align__(128) uint8_t smem[];   // the pixel ring is aligned by hand below
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FR_SM_BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FR_SM_TMEM);
+  uint8_t* wring = smem + FR_SM_W;
+  uint8_t* xring = smem + (((smem_u32(smem) + FR_SM_X + 1023u) & ~1023u) - smem_u32(smem));    // 1024-aligned
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s_begin = blockIdx.y * fd.sub_per_cta;
+  const int s_end = min(fd.n_sub, s_begin + fd.sub_per_cta);
+  // the two tile groups of the CTA; an odd tile count lets the last CTA compute its only tile twice (identical stores)
+  const int64_t tile_g0 = min(int64_t(blockIdx.x) * 2, ntiles - 1), tile_g1 = min(int64_t(blockIdx.x) * 2 + 1, ntiles - 1);
+  constexpr int NCH1 = 4 * NP1 / 32, NCH2 = 4 * NP2 / 32;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 32) {
+    for (int i = 0; i < FR_NW; ++i) { mbar_init(&bars[FRB_WFULL + i], 1); mbar_init(&bars[FRB_WFREE + i], 2); }
+    for (int g = 0; g < 2; ++g) {
+      uint64_t* gb = bars + FRB_G + g * FRB_GSTRIDE;
+      for (int i = 0; i < FR_NA; ++i) { mbar_init(&gb[FRB_AFULL + i], 4); mbar_init(&gb[FRB_AFREE + i], 1); }
+      for (int i = 0; i < 7; ++i) mbar_init(&gb[FRB_DFULL + i], 1);
+      for (int i = 0; i < FR_NX; ++i) { mbar_init(&gb[FRB_XFULL + i], 1); mbar_init(&gb[FRB_XFREE + i], 4); }
+    }
+    mbar_fence_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == 10) {
+    // ================================ producer ================================
+    if (lane == 0) {
+      Ring rw(FR_NW), rx(FR_NX);
+      auto load_pixels = [&](int pair) {
+        const int2 xy = fd.pair_xy[pair];
+        for (int g = 0; g < 2; ++g) {
+          uint64_t* gb = bars + FRB_G + g * FRB_GSTRIDE;
+          fr_wait<FR_SLEEP_PROD>(&gb[FRB_XFREE + rx.idx], rx.par ^ 1u);
+          uint8_t* dst = xring + size_t(g * FR_NX + rx.idx) * FR_XSTAGE;
+          mbar_expect_tx(&gb[FRB_XFULL + rx.idx], FR_XSTAGE);
+          if (IN_MODE == FR_IN_ROWMAJOR) {
+            fr_tensor_load(dst, &tmap, xy.x, int((g ? tile_g1 : tile_g0) * TILE), xy.y, &gb[FRB_XFULL + rx.idx]);
+          } else {
+            const uint8_t* src = xin + (size_t(g ? tile_g1 : tile_g0) * fd.in_dim + size_t(xy.y) * fd.img_w + xy.x) * TILE;
+            for (int r = 0; r < 8; ++r)
+              bulk_g2s(dst + r * 16 * TILE, src + size_t(r) * fd.img_w * TILE, 16 * TILE, &gb[FRB_XFULL + rx.idx]);
+          }
+        }
+        rx.next();
+      };
+      auto load_chunks = [&](int sub, int off, int n, int bytes) {
+        const uint8_t* src = fd.wimg + size_t(sub) * fd.sub_bytes + off;
+#pragma unroll 1
+        for (int c = 0; c < n; ++c, rw.next()) {
+          fr_wait<FR_SLEEP_PROD>(&bars[FRB_WFREE + rw.idx], rw.par ^ 1u);
+          mbar_expect_tx(&bars[FRB_WFULL + rw.idx], uint32_t(bytes));
+          bulk_g2s(wring + size_t(rw.idx) * FR_WSTAGE, src + size_t(c) * bytes, uint32_t(bytes), &bars[FRB_WFULL + rw.idx]);
+        }
+      };
+      const int cb0 = FR_HEAD + fd.nn0 * 128, cb1 = FR_HEAD + fd.nn1 * 128, cb2 = FR_HEAD + fd.nn2 * 128;
+      const int off_l1 = 4 * cb0, off_l2 = off_l1 + 2 * NCH1 * cb1;
+      load_pixels(s_begin / 2);
+      // every role walks the same 8 item slots per subtree iteration, each body instantiated once (code size: the
+      // kernel must stay inside the instruction cache):  0 L0a  1 L0b  2 L2(s-1)  3 L0c  4 L0d  5 L1ab  6 STORE(s-1)  7 L1cd
+      for (int s = s_begin; s <= s_end; ++s) {
+        const bool cur = s < s_end, prev = s > s_begin;
+        if (cur && !(s & 1) && s + 2 < s_end) load_pixels(s / 2 + 1);
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+          if (it == 6) continue;
+          const int l0 = it < 2 ? it : it - 1;
+          const bool join1 = it == 5 || it == 7;
+          const bool valid = it == 2 ? prev : cur;
+          const int sub = it == 2 ? s - 1 : s;
+          const int off = it == 2 ? off_l2 : (join1 ? off_l1 + (it == 7 ? NCH1 * cb1 : 0) : l0 * cb0);
+          const int n = it == 2 ? NCH2 : (join1 ? NCH1 : 1);
+          const int bytes = it == 2 ? cb2 : (join1 ? cb1 : cb0);
+          if (valid) load_chunks(sub, off, n, bytes);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 8) {
+    // ================================ MMA issue (one warp per tile group) ================================
+    const int g = warp - 8;
+    uint64_t* gb = bars + FRB_G + g * FRB_GSTRIDE;
+    const bool leader = elect_one();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0) + uint32_t(g * FR_GCOLS);
+    Ring rw(FR_NW), ra(FR_NA);
+    auto mma_item = [&](int nch, int nn, uint32_t dcol, int dslot, bool first_exact) {
+      const uint32_t idesc = fr_idesc(nn);
+      const uint32_t lbo = uint32_t(nn / 8) * 128u, sbo = 128u, lo_off = uint32_t(nn) * 64u;
+      const int ws0 = rw.idx;
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c, rw.next(), ra.next()) {
+        fr_wait<FR_SLEEP_MMA>(&bars[FRB_WFULL + rw.idx], rw.par);
+        fr_wait<FR_SLEEP_MMA>(&gb[FRB_AFULL + ra.idx], ra.par);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t wbase = smem_u32(wring + size_t(rw.idx) * FR_WSTAGE + FR_HEAD);
+          const uint32_t a_hi = tb + uint32_t(FR_COL_A + 32 * ra.idx), a_lo = a_hi + 16u;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint64_t bhi = tc_desc(wbase + uint32_t(2 * j) * lbo, lbo, sbo);
+            const uint64_t blo = tc_desc(wbase + lo_off + uint32_t(2 * j) * lbo, lbo, sbo);
+            fr_mma(tb + dcol, a_hi + 8u * j, bhi, idesc, (c | j) ? 1u : 0u);
+            fr_mma(tb + dcol, a_hi + 8u * j, blo, idesc, 1u);
+            if (!(first_exact && j == 0)) fr_mma(tb + dcol, a_lo + 8u * j, bhi, idesc, 1u);   // pixels are exact in FP16
+          }
+          tc_commit(&gb[FRB_AFREE + ra.idx]);
+          // the first chunk of an item carries the head the expansion warps read for every chunk: it is released last
+          if (c > 0 || nch == 1) tc_commit(&bars[FRB_WFREE + rw.idx]);
+          if (c == nch - 1) {
+            if (nch > 1) tc_commit(&bars[FRB_WFREE + ws0]);
+            tc_commit(&gb[FRB_DFULL + dslot]);
+          }
+        }
+        __syncwarp();
+      }
+    };
+    for (int s = s_begin; s <= s_end; ++s) {
+      const bool cur = s < s_end, prev = s > s_begin;
+#pragma unroll 1
+      for (int it = 0; it < 8; ++it) {
+        if (it == 6) continue;
+        const int l0 = it < 2 ? it : it - 1;
+        const bool join1 = it == 5 || it == 7;
+        const bool valid = it == 2 ? prev : cur;
+        const int nch = it == 2 ? NCH2 : (join1 ? NCH1 : 1);
+        const int nn = it == 2 ? fd.nn2 : (join1 ? fd.nn1 : fd.nn0);
+        const uint32_t dcol = it == 2 ? FR_COL_L2 : (join1 ? FR_COL_L1 + (it == 7 ? 32 : 0) : FR_COL_L0 + 16 * l0);
+        const int dslot = it == 2 ? 6 : (join1 ? (it == 7 ? 5 : 4) : l0);
+        if (valid) mma_item(nch, nn, dcol, dslot, it != 2 && !join1);
+      }
+    }
+  } else {
+    // ================================ expansion (thread = window) ================================
+    const int g = warp >> 2;
+    const int win = tid & (TILE - 1);
+    uint64_t* gb = bars + FRB_G + g * FRB_GSTRIDE;
+    const uint32_t lane_base = tbase + (uint32_t((warp & 3) * 32) << 16) + uint32_t(g * FR_GCOLS);
+    float* bias_out = reinterpret_cast<float*>(smem + FR_SM_BIAS) + warp * 32;
+    const int64_t tile = g ? tile_g1 : tile_g0;
+    Ring rw(FR_NW), ra(FR_NA), rx(FR_NX);
+
+    // Hand-over of A stages to the MMA warp.  With FR_LAZY_PUBLISH a chunk is handed over one chunk late (release() only
+    // notes that its stores were issued; the next acquire() or flush() waits for them and arrives), so that the stores
+    // complete behind the next chunk's arithmetic -- measured 3 % SLOWER (profiles/README_r02.md), hence off.
+    struct Publisher {
+      uint64_t* gb;
+      Ring& ra;
+      uint32_t lane_base;
+      int lane;
+      int pending;
+      __device__ __forceinline__ void flush() {
+        if (pending >= 0) {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&gb[FRB_AFULL + pending]);
+          pending = -1;
+        }
+      }
+      __device__ __forceinline__ uint32_t acquire() {
+        flush();
+        fr_wait(&gb[FRB_AFREE + ra.idx], ra.par ^ 1u);
+        tc_fence_after();
+        return lane_base + uint32_t(FR_COL_A + 32 * ra.idx);
+      }
+      __device__ __forceinline__ void release() {
+        pending = ra.idx;
+        ra.next();
+        if (!FR_LAZY_PUBLISH) flush();
+      }
+    } pub{gb, ra, lane_base, lane, -1};
+
+    auto head_of = [&](int stage) { return reinterpret_cast<const float*>(wring + size_t(stage) * FR_WSTAGE); };
+
+    auto item_l0 = [&](int sub, int i) {
+      const int q = sub & 1;
+      if (i == 0 && q == 0) fr_wait(&gb[FRB_XFULL + rx.idx], rx.par);
+      const uint8_t* box = xring + size_t(g * FR_NX + rx.idx) * FR_XSTAGE;
+      const int off = __ldg(fd.l0_off + sub * 4 + i);
+      const int dy = off & 0xff, dx = off >> 8;
+      float px[16];
+      if (IN_MODE == FR_IN_ROWMAJOR) {
+        // box = [8 rows][128 windows][16 bytes] (tensor dimensions ordered x, window, y): consecutive lanes read words
+        // 16 bytes apart -- 4 wavefronts per load, as many as the byte loads of the window-minor form need
+        const uint8_t* wrow = box + win * 16 + dx;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(wrow + (dy + r) * (16 * TILE));
+          const float4 f = u8x4_to_float4(u);
+          px[4 * r + 0] = f.x; px[4 * r + 1] = f.y; px[4 * r + 2] = f.z; px[4 * r + 3] = f.w;
+        }
+      } else {
+        // box = [8 rows][16 pixels][128 windows]
+        const uint8_t* col = box + (dy * 16 + dx) * TILE + win;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            px[4 * r + x] = __uint_as_float(0x4B000000u | uint32_t(col[(r * 16 + x) * TILE])) - 8388608.0f;
+      }
+      fr_wait(&bars[FRB_WFULL + rw.idx], rw.par);
+      const float* mean = head_of(rw.idx);
+      rw.next();
+      uint32_t hi[16], lo[8];
+#pragma unroll
+      for (int k = 0; k < 16; k += 4) {
+        const float4 m = *reinterpret_cast<const float4*>(mean + k);
+        hi[k / 2] = fr_pack(px[k], px[k + 1]);                 // identity terms: 8-bit integers, exact in FP16
+        hi[k / 2 + 1] = fr_pack(px[k + 2], px[k + 3]);
+        fr_split(abspow(px[k] - m.x, fd.p0), abspow(px[k + 1] - m.y, fd.p0), hi[8 + k / 2], lo[k / 2]);
+        fr_split(abspow(px[k + 2] - m.z, fd.p0), abspow(px[k + 3] - m.w, fd.p0), hi[8 + k / 2 + 1], lo[k / 2 + 1]);
+      }
+      const uint32_t col = pub.acquire();
+      tmem_st16(col, hi);
+      tmem_st8(col + 24, lo);                                  // lo pieces of the power terms (K step 1)
+      pub.release();
+      if (i == 3 && q == 1) {                                  // pixel box of the pair consumed
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gb[FRB_XFREE + rx.idx]);
+        rx.next();
+      }
+    };
+    auto item_l1 = [&](int h, uint32_t par) {
+      pub.flush();
+      fr_wait(&gb[FRB_DFULL + 2 * h], par);
+      fr_wait(&gb[FRB_DFULL + 2 * h + 1], par);
+      tc_fence_after();
+      fr_wait(&bars[FRB_WFULL + rw.idx], rw.par);
+      const float* head = head_of(rw.idx);
+      rw.advance(NCH1);
+      FrJoin<NP1>::run(lane_base + FR_COL_L0 + 32 * h, lane_base + FR_COL_L0 + 32 * h + 16, head, fd.s0, fd.clo0, fd.chi0, fd.p1, pub);
+    };
+    auto item_l2 = [&](uint32_t par) {
+      pub.flush();
+      fr_wait(&gb[FRB_DFULL + 4], par);
+      fr_wait(&gb[FRB_DFULL + 5], par);
+      tc_fence_after();
+      fr_wait(&bars[FRB_WFULL + rw.idx], rw.par);
+      const float* head = head_of(rw.idx);
+      rw.advance(NCH2);
+      __syncwarp();
+      bias_out[lane] = head[4 * NP2 + lane];                   // kept for the store item (the weight stage is recycled)
+      __syncwarp();
+      FrJoin<NP2>::run(lane_base + FR_COL_L1, lane_base + FR_COL_L1 + 32, head, fd.s1, fd.clo1, fd.chi1, fd.p2, pub);
+    };
+    auto item_store = [&](int sub, uint32_t par) {
+      pub.flush();
+      fr_wait(&gb[FRB_DFULL + 6], par);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_cols<32>(lane_base + FR_COL_L2, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float* out = xout + (size_t(tile) * fd.out_dim + __ldg(fd.out_col + sub)) * TILE + win;
+      const int nv = fd.nv_out;
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        if (k < nv) {                                          // warp-uniform: one branch per four columns
+          const float4 b = *reinterpret_cast<const float4*>(bias_out + k);
+          const float y0 = fminf(fmaxf(fmaf(__uint_as_float(r[k + 0]), fd.s2, b.x), fd.clo2), fd.chi2);
+          const float y1 = fminf(fmaxf(fmaf(__uint_as_float(r[k + 1]), fd.s2, b.y), fd.clo2), fd.chi2);
+          const float y2 = fminf(fmaxf(fmaf(__uint_as_float(r[k + 2]), fd.s2, b.z), fd.clo2), fd.chi2);
+          const float y3 = fminf(fmaxf(fmaf(__uint_as_float(r[k + 3]), fd.s2, b.w), fd.clo2), fd.chi2);
+          out[size_t(k) * TILE] = y0;
+          if (k + 1 < nv) out[size_t(k + 1) * TILE] = y1;
+          if (k + 2 < nv) out[size_t(k + 2) * TILE] = y2;
+          if (k + 3 < nv) out[size_t(k + 3) * TILE] = y3;
+        }
+      }
+    };
+
+    for (int s = s_begin; s <= s_end; ++s) {
+      const bool cur = s < s_end, prev = s > s_begin;
+      const uint32_t par = uint32_t(s - s_begin) & 1u, ppar = par ^ 1u;
+#pragma unroll 1
+      for (int it = 0; it < 8; ++it) {
+        if (it == 2) {
+          if (prev) item_l2(ppar);
+        } else if (it == 6) {
+          if (prev) item_store(s - 1, ppar);
+        } else if (cur) {
+          if (it == 5 || it == 7) item_l1(it == 7 ? 1 : 0, par);
+          else item_l0(s, it < 2 ? it : it - 1);
+        }
+      }
+    }
+    pub.flush();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+}
+
+}  // namespace hgsfa

@@ -98,6 +98,13 @@ struct Ring {
       par ^= 1u;
     }
   }
+  __device__ __forceinline__ void advance(int k) {      // k <= n
+    idx += k;
+    if (idx >= n) {
+      idx -= n;
+      par ^= 1u;
+    }
+  }
 };
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -30,6 +30,9 @@ class GpuFlow(object):
         self.input_dim = self.spec.input_dim
         self.output_dim = self.spec.output_dim
         self._node_cache = {}
+        # layers 0-2 fused into one lane-resident kernel for uint8 inputs (front.py); why not, otherwise
+        self.fused_front = getattr(self.spec, "front", None) is not None
+        self.front_reason = getattr(self.spec, "front_reason", "")
 
     # ---- mdp.Flow surface -------------------------------------------------------------------
     @property
@@ -152,7 +155,8 @@ class GpuFlow(object):
         ms, alg, exe = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
         eng = (C.c_int32 * n)()
         _lib.check(_lib.load().hgsfa_plan_op_stats(self._handle, n, ms, C.cast(eng, C.c_void_p), alg, exe))
-        return [dict(ms=ms[i], engine="tc" if eng[i] else "ffma", alg_flops=alg[i], exe_flops=exe[i]) for i in range(n)]
+        names = {0: "ffma", 1: "tc", 2: "front"}     # "front": layers 0-2 fused in one kernel, time booked on op 0
+        return [dict(ms=ms[i], engine=names.get(eng[i], "?"), alg_flops=alg[i], exe_flops=exe[i]) for i in range(n)]
 
     def set_chunks(self, front=0, back=0):
         _lib.check(_lib.load().hgsfa_plan_set_chunks(self._handle, int(front), int(back)))

@@ -976,11 +976,36 @@ def _arr(a, dtype):
     return _pad16(np.ascontiguousarray(a, dtype=dtype).tobytes())
 
 
+FRONT = _os.environ.get("HGSFA_FRONT", "1") != "0"
+
+
+def plan_front(spec):
+    """Fused-front description of the first three ops (``front.FrontSpec``) or None; the reason is kept in
+    ``spec.front_reason``.  Only the tensor-core engine fuses (``HGSFA_ENGINE=ffma`` stays the exact-FP32 path)."""
+    from . import front as _front
+    spec.front, spec.front_reason = None, "disabled"
+    if FRONT and ENGINE in ("auto", "tc") and all(op.engine == "tc" for op in spec.ops[:3]):
+        spec.front, spec.front_reason = _front.try_build(spec)
+    return spec.front
+
+
 def serialize(spec):
-    """Plan blob, version 2 (parsed by hgsfa_plan_create in csrc/flow.cu; layout in DESIGN.md section 4)."""
+    """Plan blob, version 2 (parsed by hgsfa_plan_create in csrc/flow.cu; layout in DESIGN.md section 4).
+    Header: magic, input_dim, last op's out_dim, n_ops, byte offset and size of the fused-front section (0 = none)."""
+    from . import front as _front
     last_dim = spec.ops[-1].out_dim
-    out = [b"HGSFAPL2" + struct.pack("<7q", spec.input_dim, last_dim, len(spec.ops), 0, 0, 0, 0)]
-    assert len(out[0]) == 64
+    body = _serialize_ops(spec)
+    fr = getattr(spec, "front", None)
+    if fr is None and not hasattr(spec, "front_reason"):
+        fr = plan_front(spec)
+    fsec = _front.serialize(fr) if fr is not None else b""
+    hdr = b"HGSFAPL2" + struct.pack("<7q", spec.input_dim, last_dim, len(spec.ops), (64 + len(body)) if fsec else 0, len(fsec), 0, 0)
+    assert len(hdr) == 64 and len(body) % 16 == 0
+    return hdr + body + fsec
+
+
+def _serialize_ops(spec):
+    out = []
     for op in spec.ops:
         n_w = 1 if op.shared else op.n_nodes
         n_terms = sum(ps["K"] for ps in op.passes)

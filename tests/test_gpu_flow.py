@@ -64,14 +64,70 @@ def test_u11l_both_engines(u11l_flow, engine, monkeypatch):
     monkeypatch.setattr(plan, "ENGINE", engine)
     g = GpuFlow(u11l_flow)
     assert {op.engine for op in g.spec.ops} == {engine}
+    assert g.fused_front == (engine == "tc")          # the FP32 engine never fuses: it is the exact-FP32 option
     x = synthetic.synthetic_patches(384, (64, 64), 21)
     e = _check(g, u11l_flow, x, std=u11l_flow._train_output_std, tol=(2e-5 if engine == "ffma" else TOL))
     print("U11L_64 engine", engine, "max err/std", e)
     g.profile(True)
     g.execute(x)
     st = g.op_stats()
-    assert len(st) == 11 and all(s["engine"] == engine and s["ms"] > 0 for s in st)
+    assert len(st) == 11
+    if engine == "tc":      # uint8 windows: layers 0-2 run as one fused launch whose time is booked on op 0
+        assert [s["engine"] for s in st] == ["front"] * 3 + ["tc"] * 8
+        assert st[0]["ms"] > 0 and st[1]["ms"] == 0 and st[2]["ms"] == 0 and all(s["ms"] > 0 for s in st[3:])
+    else:
+        assert all(s["engine"] == engine and s["ms"] > 0 for s in st)
     g.close()
+
+
+def test_fused_front_matches_per_layer_path(u11l_flow, monkeypatch):
+    """Layers 0-2 fused in one lane-resident kernel (csrc/front_tc.cuh, FP16-split tcgen05) against the same flow
+    run layer by layer (HGSFA_FRONT=0), for row-major and window-minor uint8 input, ragged window counts, the host
+    entry point, and float inputs (which keep the per-layer path)."""
+    import ctypes as C
+    import torch
+    from pyfaceanalysis_b200 import GpuFlow, _lib, synthetic
+    fused = GpuFlow(u11l_flow)
+    monkeypatch.setenv("HGSFA_FRONT", "0")          # read by hgsfa_plan_create
+    plain = GpuFlow(u11l_flow)
+    monkeypatch.delenv("HGSFA_FRONT")
+    assert fused.fused_front and fused.front_reason == ""
+    fused.profile(True)
+    plain.profile(True)
+    std = u11l_flow._train_output_std
+    rng = np.random.default_rng(5)
+    for n in (1, 127, 129, 1000):
+        x = np.concatenate([synthetic.synthetic_patches(n // 2 + 1, (64, 64), 40 + n),
+                            rng.integers(0, 256, (n, 4096), dtype=np.uint8)])[:n]
+        xt = torch.as_tensor(x, device="cuda")
+        y_p = plain.execute_torch(xt).cpu().numpy().astype(np.float64)
+        y_f = fused.execute_torch(xt).cpu().numpy().astype(np.float64)
+        tiled = torch.zeros((n + 127) // 128 * 128 * 4096, dtype=torch.uint8, device="cuda")
+        _lib.check(_lib.load().hgsfa_tile_windows_device(C.c_void_p(xt.data_ptr()), _lib.U8, n, 4096, 4096,
+                                                         C.c_void_p(tiled.data_ptr()), _lib.U8, None))
+        y_t = fused.execute_torch(tiled, layout=_lib.TILED, n=n).cpu().numpy().astype(np.float64)
+        assert np.array_equal(y_t, y_f)                     # both input layouts feed the same arithmetic
+        sd = np.maximum(std, y_p.std(axis=0)) if n > 1 else std
+        assert (np.abs(y_f - y_p) / sd).max() <= TOL, n
+        if n <= 129:
+            ref = onodes.flow_execute(u11l_flow, x.astype(np.float64))
+            assert (np.abs(y_f - ref) / sd).max() <= TOL, n
+        # rows whose pitch is not 16-byte aligned cannot go through the tensor map: tiled first, same kernel
+        if n > 1:
+            wide = torch.zeros((n, 4099), dtype=torch.uint8, device="cuda")
+            wide[:, :4096] = xt
+            y_w = fused.execute_torch(wide[:, :4096]).cpu().numpy().astype(np.float64)
+            assert np.array_equal(y_w, y_f)
+    assert [s["engine"] for s in fused.op_stats()][:4] == ["front", "front", "front", "tc"]
+    assert [s["engine"] for s in plain.op_stats()][:3] == ["tc", "tc", "tc"] and plain.op_stats()[1]["ms"] > 0
+    # host entry point (pieces through the staging buffers) and float input (per-layer path, exact same values as `plain`)
+    xh = rng.integers(0, 256, (70000, 4096), dtype=np.uint8)
+    y_f, y_p = fused.execute(xh, out_dtype=np.float32), plain.execute(xh, out_dtype=np.float32)
+    assert (np.abs(y_f.astype(np.float64) - y_p) / np.maximum(std, y_p.std(axis=0))).max() <= TOL
+    xf = xh[:300].astype(np.float32)
+    assert np.array_equal(fused.execute(xf), plain.execute(xf))
+    fused.close()
+    plain.close()
 
 
 def test_u11l_parity_uniform_noise(u11l_flow):

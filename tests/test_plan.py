@@ -252,3 +252,29 @@ def test_igsfa_lr_input_switch(monkeypatch, mode, lr_input):
     ref = onodes.flow_execute([_layer(nodes)], x)
     assert (lr_input == "scaled") == bool(np.allclose(ref, ref_scaled))
     assert np.allclose(ref[:, :3], ref_scaled[:, :3])       # the slow part is the same under both readings
+
+
+def test_fused_front_tables_match_unfused_ops(u11l_flow):
+    """The fused front (layers 0-2 in one kernel) streams its own weight chunks and tables; executed in numpy the way
+    the kernel walks them they reproduce the three unfused ops (FP16 hi + lo weights: 22 bits)."""
+    import front_interp
+    from pyfaceanalysis_b200 import front
+    spec = plan.compile_flow(u11l_flow)
+    f = plan.plan_front(spec)
+    assert f is not None, spec.front_reason
+    assert (f.n_sub, f.np1, f.np2, f.nn, f.nch) == (64, 16, 24, (16, 32, 32), (1, 2, 3))
+    x = synthetic.synthetic_patches(6, (64, 64), 7).astype(np.float64)
+    ref = x
+    for op in spec.ops[:3]:
+        ref = plan_interp.run_op(op, ref)
+    got = front_interp.run_front(f, x)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    blob = plan.serialize(spec)
+    off, size = struct.unpack("<2q", blob[32:48])
+    assert off % 16 == 0 and off + size == len(blob) and blob[off:off + 8] == front.MAGIC
+    # flows that do not match the pattern keep the per-layer path and say why
+    tiny = synthetic.cached_flow("tiny", seed=0)
+    ts = plan.compile_flow(tiny)
+    assert plan.plan_front(ts) is None and ts.front_reason
+    assert struct.unpack("<2q", plan.serialize(ts)[32:48]) == (0, 0)

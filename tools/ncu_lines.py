@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 
-def main(path, top=40, kernel="regex:layer_"):
+def main(path, top=40, kernel="regex:layer_|front_"):
     raw = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", kernel,
                           "--launch-count", "1"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
