@@ -14,9 +14,13 @@ uniform integers 0..255, seed 12345600 (FaceDetectUpdated.py:146).  One step = o
   e2e   : the same through the public drop-in call GpuFlow.execute(x) with x in pinned HOST memory:
           host->device copy of the windows and device->host copy of the (N, 60) float64 features are
           inside the timed region
-  roofline : dominant kernel of the step (DESIGN.md section 6): hgsfa::layer_tc_kernel (tcgen05 3xTF32) against
-          measured bf16 peak / 6, or hgsfa::layer_kernel (packed FP32 FMA) against the measured FFMA2 peak;
-          achieved = algorithmic flops of that kernel's ops / its CUDA-event time inside the timed steps
+  roofline : dominant kernel of the step (DESIGN.md section 6): hgsfa::front_kernel (layers 0-2 fused, tcgen05 kind::f16,
+          2-piece FP16 split: ceiling = measured bf16 peak / 3), hgsfa::layer_tc_kernel (tcgen05 3xTF32: bf16 peak / 6)
+          or hgsfa::layer_kernel (packed FP32 FMA: measured FFMA2 peak); achieved = algorithmic flops of that kernel's
+          ops / its CUDA-event time inside the timed steps; every kernel of the step is listed under "kernels"
+  detect : BASELINE configs[2] on the same clock -- 64 synthetic 1920x1080 images per GPU, smallest_face 0.05,
+          images/s with upload, device prescale, 17 face stages + eye stage, host purge and the gather of the
+          detection lists inside the timed region; images are sharded over the ranks (pyfaceanalysis_b200/shard.py)
   cpu_baseline : the float64 numpy oracle (the reference cannot run: Python 2 + un-vendored mdp /
           cuicuilco) on a bounded sample on the box's host cores, BLAS threads = min(12, nproc)
           (FaceDetectUpdated.py:74)
@@ -70,19 +74,22 @@ def _fp32_peak():
 
 def _traffic_per_window():
     """DRAM bytes per window of the layer kernels, from the committed ncu launch list (profiles/)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
-            t = json.load(f)
-        return float(t["layer_dram_bytes_per_window"]), t["source"], float(t["layer_share_of_step"])
-    except Exception:
-        return None, None, None
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            return float(t["layer_dram_bytes_per_window"]), t["source"], float(t["layer_share_of_step"])
+        except Exception:
+            continue
+    return None, None, None
 
 
 def _roofline(op_stats, steps, n, fl, kernel_ms_last, peaks, fp32_peak, fp32_src, traffic, tsrc, lshare):
-    """Roofline of the dominant kernel of a step.  The layer ops run on one of two kernels:
-    hgsfa::layer_tc_kernel (tcgen05, 3xTF32: three TF32 MMAs per algorithmic multiply-add block, TF32 at half the
-    bf16 rate -> ceiling = measured bf16 peak / 6 in algorithmic flops) and hgsfa::layer_kernel (packed FP32 FMA).
-    Times are CUDA-event totals per op over the timed steps, on the launching stream."""
+    """Roofline of the dominant kernel of a step, plus every kernel of the step under "kernels" (DESIGN.md section 6):
+    hgsfa::front_kernel (layers 0-2 in one launch, 2-piece FP16 split on tcgen05 kind::f16: three bf16-rate MMAs per
+    algorithmic block -> ceiling = measured bf16 peak / 3), hgsfa::layer_tc_kernel (3xTF32 at half the bf16 rate:
+    peak / 6) and hgsfa::layer_kernel (packed FP32 FMA).  Times are CUDA-event totals per op over the timed steps, on
+    the launching stream; flops are the algorithmic ones of SURVEY.md 8d (hgsfa_plan_flops)."""
     eng = {}
     for st in op_stats:
         e = eng.setdefault(st["engine"], dict(ms=0.0, alg=0.0, exe=0.0, ops=0))
@@ -93,26 +100,28 @@ def _roofline(op_stats, steps, n, fl, kernel_ms_last, peaks, fp32_peak, fp32_src
     for e in eng.values():
         e["achieved"] = e["alg"] / (e["ms"] * 1e-3) / 1e12 if e["ms"] > 0 else None
     bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-    tc_peak = bf16 / 6.0
-    dom = max(eng, key=lambda k: eng[k]["ms"]) if eng else "ffma"
+    bf16_txt = "%s bf16 %s %.1f TFLOP/s" % (peaks["_source"], "sustained" if "bf16_tflops_sustained" in peaks else "burst", bf16)
+    ceilings = {
+        "front": ("hgsfa::front_kernel (layers 0-2 fused, lane-resident; tcgen05 kind::f16)", "tensor", bf16 / 3.0,
+                  bf16_txt + " / 3 (2-piece FP16 split = 3 MMAs per algorithmic block)"),
+        "tc": ("hgsfa::layer_tc_kernel (tcgen05 kind::tf32)", "tensor", bf16 / 6.0,
+               bf16_txt + " / 6 (TF32 = bf16 / 2; 3xTF32 split = 3 MMAs per algorithmic block)"),
+        "ffma": ("hgsfa::layer_kernel (packed FP32 FMA)", "fp32", fp32_peak, fp32_src)}
+    kernels = []
+    for name, e in eng.items():
+        kname, bound, peak, src = ceilings[name]
+        a = e["achieved"]
+        kernels.append({"kernel": kname, "ops": e["ops"], "ms_per_step": e["ms"], "bound": bound, "achieved": a, "peak": peak,
+                        "unit": "TFLOP/s", "frac": a / peak if a else None, "peak_source": src,
+                        "algorithmic_flops_per_window": e["alg"] / n, "executed_pipe_flops_per_step": e["exe"]})
+    kernels.sort(key=lambda k: -k["ms_per_step"])
+    dom = kernels[0] if kernels else None
     out = {}
-    if dom == "tc":
-        a = eng["tc"]["achieved"]
-        out = {"bound": "tensor", "achieved": a, "peak": tc_peak, "unit": "TFLOP/s", "frac": a / tc_peak if a else None,
-               "kernel": "hgsfa::layer_tc_kernel (%d of %d layer ops, %.1f of %.1f ms per step)"
-                         % (eng["tc"]["ops"], len(op_stats), eng["tc"]["ms"], kernel_ms_last),
-               "peak_source": "%s bf16 %s %.1f TFLOP/s / 6 (TF32 = bf16 / 2; 3xTF32 split = 3 MMAs per algorithmic block)"
-                              % (peaks["_source"], "sustained" if "bf16_tflops_sustained" in peaks else "burst", bf16),
-               "tensor_pipe_flops_per_step": eng["tc"]["exe"]}
-    else:
-        a = eng.get("ffma", {}).get("achieved")
-        out = {"bound": "fp32", "achieved": a, "peak": fp32_peak, "unit": "TFLOP/s", "frac": a / fp32_peak if a else None,
-               "kernel": "hgsfa::layer_kernel", "peak_source": fp32_src}
-    if "ffma" in eng and dom == "tc":
-        a = eng["ffma"]["achieved"]
-        out["ffma_kernel"] = {"kernel": "hgsfa::layer_kernel (%d ops, %.1f ms per step)" % (eng["ffma"]["ops"], eng["ffma"]["ms"]),
-                              "bound": "fp32", "achieved": a, "peak": fp32_peak, "frac": a / fp32_peak if a else None,
-                              "peak_source": fp32_src}
+    if dom:
+        out = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"],
+               "kernel": "%s: %d of %d layer ops, %.1f of %.1f ms per step" % (dom["kernel"], dom["ops"], len(op_stats),
+                                                                              dom["ms_per_step"], kernel_ms_last),
+               "peak_source": dom["peak_source"], "kernels": kernels}
     whole = fl["algorithmic"] / (kernel_ms_last * 1e-3) / 1e12 if kernel_ms_last > 0 else None
     out.update({
         "traffic": (traffic * n) if traffic else None, "traffic_unit": "DRAM bytes per step, all layer launches (ncu)",
@@ -196,6 +205,142 @@ class ClockSampler(object):
         return out
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# detection leg: BASELINE configs[2] (default) / configs[4] (--detect-config 4)
+# ------------------------------------------------------------------------------------------------------------------
+DETECT_CONFIGS = {
+    2: dict(name="configs[2]", hw=(1080, 1920), smallest_face=0.05, prescale=True, images=64),
+    4: dict(name="configs[4]", hw=(2160, 3840), smallest_face=0.02, prescale=False, images=21),
+}
+
+
+class _StageTimes(object):
+    """The add_task_ellapsed surface of the reference's benchmarking.Benchmark: device seconds per label."""
+
+    def __init__(self):
+        self.tasks = {}
+
+    def add_task_ellapsed(self, task_label, ellapsed_time, reference=None):
+        t, k = self.tasks.get(task_label, (0.0, 0))
+        self.tasks[task_label] = (t + ellapsed_time, k + 1)
+
+
+def _detect_scenes(cm, cfg, n_bases=8):
+    """Deterministic synthetic scenes (smooth noise + face-like blobs); a rank's images are shifted copies of these."""
+    H, W = cfg["hw"]
+    bases = []
+    for b in range(n_bases):
+        rng = np.random.default_rng(9000 + b)
+        s = min(H, W)
+        faces = [(rng.uniform(0.1 * W, 0.9 * W), rng.uniform(0.15 * H, 0.85 * H), rng.uniform(0.07 * s, 0.3 * s), rng.uniform(-10, 10))
+                 for _ in range(4)]
+        bases.append(cm.render_scene(H, W, faces, 9100 + b))
+    return bases
+
+
+def run_detect(args, rank, world, local_rank, dev, barrier, dist):
+    """images/s of the full detection path on synthetic images, sharded by image over the ranks (weak scaling: every rank
+    owns `images` images).  Timed region per step: pinned host images -> device, NEAREST prescale (FaceDetectUpdated.py:551),
+    window pyramid, 17 face stages, eye stage, host purge, and the gather of the per-image detection lists."""
+    import torch
+    from threadpoolctl import threadpool_limits
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cascade_models as cm                       # synthetic model set (flows + heads); cached under build/flows
+    from pyfaceanalysis_b200 import GpuFlow, GpuGaussianClassifier, shard
+    from pyfaceanalysis_b200.cascade import FaceDetector
+    cfg = DETECT_CONFIGS[args.detect_config]
+    m = cm.cached_models(spec=FLOW_SPEC)
+    flows, heads = {}, {}
+    nets = [None if f is None else flows.setdefault(id(f), GpuFlow(f, device=local_rank)) for f in m["networks"]]
+    clfs = [None if c is None else heads.setdefault(id(c), GpuGaussianClassifier(c, device=local_rank)) for c in m["classifiers"]]
+    n_img = args.detect_images or cfg["images"]
+    total = n_img * world
+    mine = shard.image_shard(total, rank, world)                     # round robin over the global image list
+    base = _detect_scenes(cm, cfg, min(8, n_img))
+    host = [torch.from_numpy(np.ascontiguousarray(np.roll(base[k % len(base)], (k * 37) % cfg["hw"][1], axis=1))).pin_memory()
+            for k in mine]                                            # image k of the global list: base k % 8 shifted by 37 k columns
+    # The synthetic heads are not trained to the reference's operating point: calibrate the Disc cut-offs on one image
+    # (the same on every rank) so that the funnel has the shape a cascade is built for: few windows survive Disc1.
+    keep = {"Disc1": 0.04, "Disc3": 0.4, "Disc5": 0.5, "Disc7": 0.6, "Disc9": 0.5}
+    cut = [1e30] * 10
+    cal = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=cut, header_eye=None, device=local_rank)
+    cal_img = cal.prescale([torch.from_numpy(base[0]).to(dev)])[0] if cfg["prescale"] else torch.from_numpy(base[0]).to(dev)
+    for name, frac in keep.items():
+        cal.cut_offs = list(cut)
+        _, tr0 = cal.detect([cal_img], smallest_face=cfg["smallest_face"], return_trace=True)
+        sc = tr0["disc_scores"].get(name)
+        cut[int(name[-1])] = float(np.nanquantile(sc, frac)) if sc is not None and len(sc) else 0.0
+    det = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=cut, header_eye=m["header_eye"], device=local_rank)
+
+    def step(bench=None):
+        imgs = [h.to(dev, non_blocking=True) for h in host]
+        if cfg["prescale"]:
+            imgs = det.prescale(imgs)
+        local, tr = det.detect(imgs, smallest_face=cfg["smallest_face"], return_trace=True, benchmark=bench)
+        allr = shard.gather_detections(local, mine, total)            # per-image lists, host objects, every rank
+        return allr, tr
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        allr, tr = step()
+    torch.cuda.synchronize(dev)
+    barrier()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        allr, tr = step()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item()) / steps
+    stage_bench = _StageTimes()
+    step(stage_bench)                                                 # one more, untimed, with device times per label
+    res = None
+    if rank == 0:
+        peaks = _peaks()
+        crops = [int(tr["stage_counts"][k]) for k in range(len(det.types)) if det.networks[k] is not None and
+                 not (k > 0 and det.types[k - 1][:-1] == "Disc")]
+        crop_s = stage_bench.tasks.get("Extraction of subimages patches", (0.0, 0))[0]
+        crop_bytes = float(sum(crops)) * 4096 * 2
+        res = {"metric": "detect images/sec", "value": total / dt, "unit": "images/s", "ms_per_batch": dt * 1e3, "n_gpus": world,
+               "scaling": "weak", "images_per_gpu": n_img, "images_total": total, "steps": steps,
+               "config": {"workload": "%s: %d synthetic %dx%d 'L' images per GPU, smallest_face %.2f, %s, synthetic %s cascade "
+                                      "(17 face stages + eye stage + purge)" % (cfg["name"], n_img, cfg["hw"][1], cfg["hw"][0],
+                                                                               cfg["smallest_face"], "NEAREST prescale to <= 1000 px on the device"
+                                                                               if cfg["prescale"] else "no prescale (--image_prescaling=0)", FLOW_SPEC),
+                          "sharding": "images round robin over ranks (shard.image_shard), detection lists gathered with "
+                                      "all_gather_object (shard.gather_detections)"},
+               "windows_per_gpu": int(tr["n_windows"]), "stage_counts": [int(c) for c in tr["stage_counts"]],
+               "detections_total": int(sum(len(o) for o in allr)), "host_syncs_per_batch": int(tr["host_syncs"]),
+               "calibrated_cut_offs": cut,
+               "e2e": {"value": total / dt, "unit": "images/s", "h2d_bytes_per_step": int(sum(h.numel() for h in host)),
+                       "d2h_bytes_per_step": int(sum(len(o) for o in allr) * 80 // max(world, 1)),
+                       "api": "FaceDetector.prescale + FaceDetector.detect on pinned host images"},
+               "stage_ms": {k: round(v[0] * 1e3, 3) for k, v in stage_bench.tasks.items()},
+               "crop_roofline": {"bound": "hbm", "kernel": "hgsfa::crop_index_kernel + crop_gather_kernel (row-major patches)",
+                                 "windows_cropped": int(sum(crops)), "achieved": crop_bytes / crop_s / 1e9 if crop_s > 0 else None,
+                                 "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": crop_bytes / crop_s / 1e9 / peaks["hbm_gbs"] if crop_s > 0 else None,
+                                 "bytes_per_window": "4096 gathered + 4096 written (SURVEY.md 8d)", "peak_source": peaks["_source"]}}
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import cascade as ocascade
+            threads = min(12, os.cpu_count() or 1)
+            img0 = cal_img.cpu().numpy()
+            with threadpool_limits(limits=threads):
+                c0 = time.perf_counter()
+                ocascade.detect_image(img0, m["header"], m["network_types"], m["networks"], m["classifiers"], cfg["smallest_face"],
+                                      m["num_face_stages"], cut_offs_face=cut, eye_header=m["header_eye"])
+                cdt = time.perf_counter() - c0
+            res["cpu_baseline"] = {"value": 1.0 / cdt, "unit": "images/s", "cores": threads, "nproc": os.cpu_count(), "kind": "port",
+                                   "sample": "1 image (%d windows), float64 numpy oracle of the reference loop, %.1f s"
+                                             % (int(tr["n_windows"]) // n_img, cdt)}
+    for g in flows.values():
+        g.close()
+    return res
+
+
+
 def cpu_oracle_windows_per_s(flow, n_sample, threads, reps=1):
     """The float64 numpy restatement (oracle/) on host cores: the 'port' CPU baseline."""
     from oracle import nodes as onodes
@@ -240,7 +385,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "U11L_64 flow forward, bounded CPU sample of configs[1]", "windows_per_step": n_sample,
                    "window_dim": 4096},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "nproc": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -257,6 +402,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--front-chunk", type=int, default=0, help="windows per front-segment chunk (0 = library default)")
     ap.add_argument("--back-chunk", type=int, default=0)
+    ap.add_argument("--no-detect", action="store_true", help="skip the detection leg (BASELINE configs[2])")
+    ap.add_argument("--detect-config", type=int, default=2, choices=sorted(DETECT_CONFIGS), help="2: 64 x 1920x1080 prescaled; "
+                    "4: 21 x 3840x2160 without prescale (~1e6 windows per GPU)")
+    ap.add_argument("--detect-images", type=int, default=0, help="images per GPU (0 = the config's)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
@@ -366,6 +515,12 @@ def main():
             raise SystemExit("bench: device-resident and host-path results differ")
         del x_host, y_host
 
+    detect = None
+    if not args.no_detect:
+        del x_dev, y_dev
+        torch.cuda.empty_cache()
+        detect = run_detect(args, rank, world, local_rank, dev, barrier, dist if world > 1 else None)
+
     if rank == 0:
         fl = g.flops(n)
         fp32_peak, fp32_src = _fp32_peak()
@@ -374,7 +529,7 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (FFMA ops) / 3xtf32 with f32 accumulation (tensor-core ops)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f16x2 split (fused front) / 3xtf32 (layer ops), f32 accumulation; f32 FFMA with HGSFA_ENGINE=ffma", "data": "synthetic",
             "config": {"workload": "configs[1]: U11L_64 (FaceCentering2-shaped synthetic HiGSFA flow) forward, "
                                    "%d windows x 4096 uint8 per GPU per step" % n,
                        "windows_per_gpu": n, "window_dim": g.input_dim, "features": F, "flow": FLOW_SPEC,
@@ -387,11 +542,13 @@ def main():
                        "samples": clocks["samples"], "window": clocks.get("window")},
             "roofline": _roofline(op_stats, args.steps, n, fl, kernel_ms_last, peaks, fp32_peak, fp32_src, tpw, tsrc, lshare),
         }
+        if detect is not None:
+            out["detect"] = detect
         if not args.no_cpu_baseline:
             threads = min(12, os.cpu_count() or 1)
             n_sample = 32768
             v, secs = cpu_oracle_windows_per_s(flow, n_sample, threads)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "nproc": os.cpu_count(), "kind": "port",
                                    "sample": "%d windows x 4096 px (same distribution), float64 numpy oracle, %.1f s"
                                              % (n_sample, secs)}
         print(json.dumps(out))

@@ -8,9 +8,11 @@ every per-window array.
 
 Here the windows of ALL scales of ALL images of a batch travel through the stages together, resident on
 the device: grid coordinates are uploaded once, crop -> flow -> head -> controller -> compaction are
-kernels of ``libhgsfa.so``, and the only per-stage host round trip is the 8-byte survivor count.  Windows
-are independent until the per-image purge, so batching changes nothing but the order of evaluation; the
-stable compaction keeps the reference's order (image, scale, window) inside the batch.
+kernels of ``libhgsfa.so``.  Windows are independent until the per-image purge, so batching changes nothing but
+the order of evaluation, and a window a stage discards may simply stay in the batch (its results are never
+read): the arrays are compacted -- an 8-byte survivor count read by the host -- only after a Disc stage
+that still holds many windows (in practice once, after Disc1), and at the end.  The stable compaction
+keeps the reference's order (image, scale, window) inside the batch.
 
 After the face stages the eyes of every surviving face are refined with the eye network and its two heads
 (``FaceDetectUpdated.py:946-1041`` -> ``find_Left_Right_eyes``, ``face_analysis.py:1036-1109``): rotated 64x64 crops
@@ -19,7 +21,8 @@ of the two eye boxes, per-patch contrast normalisation ("AgeContrastEnhancement_
 on the same input), EyeLX / EyeLY regressions, |reg| >= 9 discards the face.  Without eye networks the detections
 carry the approximate eye positions of ``compute_approximate_eye_boxes_coordinates``.
 
-What is NOT here yet: the age / race / gender stage (``normalize_image`` needs BICUBIC resampling).
+Front end: ``prescale`` (NEAREST resize to <= 1000 px, ``FaceDetectUpdated.py:551-559``) runs on the device; back end:
+``format_detections`` writes the reference's result lines (``FaceDetectUpdated.py:1258-1278``).
 """
 from __future__ import annotations
 
@@ -104,6 +107,22 @@ def purge_detections(det, weight_confidences_by_area=True):
     return det[unique].copy()
 
 
+def format_detections(det, right_screen_eye_first=False, attributes=None):
+    """Result lines of one image exactly as ``FaceDetectUpdated.py:1258-1278`` writes them:
+    ``"%d, %d, %d, %d, %f, %d, %d, %d, %d"`` of the rounded box, the angle and the rounded eye coordinates (left / right
+    swapped with ``right_screen_eye_first``), optionally ``", %2.1f, %s, %s, %f"`` of age, race, gender and confidence
+    (``attributes`` = (ages, races, genders), ``write_age_race_gender_confidence``), then ``" \\n"``."""
+    lines = []
+    for j, row in enumerate(np.asarray(det, dtype=np.float64).reshape(-1, 10)):
+        r = np.round(row[0:9])
+        eyes = (r[7], r[8], r[5], r[6]) if right_screen_eye_first else (r[5], r[6], r[7], r[8])
+        line = "%d, %d, %d, %d, %f, %d, %d, %d, %d" % ((r[0], r[1], r[2], r[3], row[4]) + eyes)
+        if attributes is not None:
+            line += ", %2.1f, %s, %s, %f" % (attributes[0][j], attributes[1][j], attributes[2][j], row[9])
+        lines.append(line + " \n")
+    return "".join(lines)
+
+
 class FaceDetector(object):
     """The face stages of a pipeline (``network_types[:num_networks - 5]``) as one device-resident cascade.
 
@@ -129,6 +148,9 @@ class FaceDetector(object):
         if self.networks and self.networks[0] is None:
             raise ValueError("the first stage needs a network")
         self._labels = {}
+        # windows above which a Disc stage is followed by a compaction (one host round trip); below it discarded windows
+        # simply ride along
+        self.lazy_threshold = int(self.cfg.get("lazy_threshold", 32768))
         # eye stage: network_types[n_stages] = EyeLX, [n_stages + 1] = EyeLY (same flow file, two heads)
         self.header_eye = tuple(header_eye) if header_eye is not None else None
         self.eye_net = None
@@ -201,16 +223,60 @@ class FaceDetector(object):
             cache[key] = p
         return p
 
-    def detect(self, images, smallest_face=0.2, return_trace=False):
-        """images: list of 2-D uint8 arrays (the reference's mode-'L' image, already prescaled).
-        Returns a list (one entry per image) of (M,10) float64 detection arrays after the purge; with
-        ``return_trace`` also a dict with the per-stage window counts and the un-purged detections."""
+    def prescale(self, images, prescale_size=None):
+        """The reference's NEAREST prescale to at most ``prescale_size`` pixels per side (``FaceDetectUpdated.py:551-559``:
+        ``factor = max(w / 1000., h / 1000.)``; if > 1: ``resize((int(w / factor), int(h / factor)), Image.NEAREST)``),
+        on the device: Pillow's NEAREST resize is the EXTENT transform of the whole image, i.e. one window per image
+        for the crop kernel.  images: 2-D uint8 numpy arrays or CUDA tensors; returns a list of CUDA uint8 tensors."""
+        torch = self.torch
+        lib = _lib.load()
+        size = float(self.cfg["prescale_size"] if prescale_size is None else prescale_size)
+        out = [None] * len(images)
+        with torch.cuda.device(self.dev):
+            stream = torch.cuda.current_stream(self.dev).cuda_stream
+            sp = C.c_void_p(stream) if stream else None
+            groups = {}                                        # images of one size are resized by ONE launch
+            for k, im in enumerate(images):
+                t = im if torch.is_tensor(im) else torch.as_tensor(np.ascontiguousarray(im, dtype=np.uint8), device=self.dev)
+                h, w = int(t.shape[0]), int(t.shape[1])
+                factor = max(w * 1.0 / size, h * 1.0 / size)
+                if factor > 1.0:
+                    groups.setdefault((h, w, int(w / factor), int(h / factor)), []).append((k, t))
+                else:
+                    out[k] = t
+            for (h, w, pw, ph), items in groups.items():
+                if pw > 1024 or ph > 1024:
+                    raise ValueError("prescaled size %dx%d exceeds the crop kernel's 1024-pixel patch limit" % (pw, ph))
+                n = len(items)
+                key = ("prescale", h, w, n)
+                cache = self.__dict__.setdefault("_prescale_cache", {})
+                if key not in cache:
+                    cache[key] = (torch.tensor([[0.0, 0.0, float(w), float(h)]] * n, dtype=torch.float64, device=self.dev),
+                                  torch.tensor([[h, w]] * n, dtype=torch.int32, device=self.dev),
+                                  torch.arange(n, dtype=torch.int32, device=self.dev))
+                boxes, hw, idx = cache[key]
+                ptrs = torch.tensor([t.data_ptr() for _, t in items], dtype=torch.int64, device=self.dev)
+                dst = torch.empty((n, ph, pw), dtype=torch.uint8, device=self.dev)
+                _lib.check(lib.hgsfa_crop_extent_batch_device(
+                    C.c_void_p(ptrs.data_ptr()), C.c_void_p(hw.data_ptr()), C.c_void_p(idx.data_ptr()), C.c_void_p(boxes.data_ptr()),
+                    None, n, pw, ph, _lib.NEAREST, C.c_void_p(dst.data_ptr()), _lib.U8, _lib.ROWMAJOR, sp))
+                for j, (k, _) in enumerate(items):
+                    out[k] = dst[j]
+        return out
+
+    def detect(self, images, smallest_face=0.2, return_trace=False, benchmark=None):
+        """images: list of 2-D uint8 arrays (the reference's mode-'L' image, already prescaled) or CUDA uint8 tensors
+        (e.g. from ``prescale``).  Returns a list (one entry per image) of (M,10) float64 detection arrays after the
+        purge; with ``return_trace`` also a dict with the per-stage window counts and the un-purged detections.
+        ``benchmark``: an object with the reference's ``Benchmark.add_task_ellapsed(label, seconds)``
+        (``benchmarking.py:39``); it receives the device time of every phase under the reference's labels
+        (``FaceDetectUpdated.py:691,711,724,760``), summed over the stages of the batch."""
         # the detector's device becomes current for the call: torch allocations, the stream looked up below and
         # every kernel launch then agree, whatever device the calling thread had selected
         with self.torch.cuda.device(self.dev):
-            return self._detect(images, smallest_face, return_trace)
+            return self._detect(images, smallest_face, return_trace, benchmark)
 
-    def _detect(self, images, smallest_face, return_trace):
+    def _detect(self, images, smallest_face, return_trace, benchmark):
         torch = self.torch
         lib = _lib.load()
         dev = self.dev
@@ -219,24 +285,37 @@ class FaceDetector(object):
         sp = C.c_void_p(stream) if stream else None
         prof = {} if os.environ.get("HGSFA_DETECT_PROFILE") else None      # phase -> seconds (synchronising: diagnostics only)
         t_last = [time.perf_counter()]
+        marks = [] if benchmark is not None else None                      # (label, event): device times, read once at the end
 
-        def mark(name):
+        def mark(name, label=None):
+            if marks is not None and label is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((label, ev))
             if prof is not None:
                 torch.cuda.synchronize(dev)
                 now = time.perf_counter()
                 prof[name] = prof.get(name, 0.0) + now - t_last[0]
                 t_last[0] = now
 
+        mark("start", "")
         # ---- window pyramid of every image, one batch ----
-        pyr = [self._pyramid(im.shape[1], im.shape[0], smallest_face) for im in images]
+        shapes = [(int(im.shape[0]), int(im.shape[1])) for im in images]
+        pyr = [self._pyramid(w, h, smallest_face) for h, w in shapes]
         n0 = int(sum(len(p["coords"]) for p in pyr))
-        counts = np.zeros(len(self.types), dtype=np.int64)
+        n_stages = len(self.types)
         if n0 == 0:
             out = [np.zeros((0, 10)) for _ in images]
-            return (out, dict(stage_counts=counts, raw=[np.zeros((0, 10)) for _ in images])) if return_trace else out
+            tr = dict(stage_counts=np.zeros(n_stages, dtype=np.int64), raw=[np.zeros((0, 10)) for _ in images], n_windows=0,
+                      disc_scores={}, host_syncs=0)
+            return (out, tr) if return_trace else out
         scale_h = np.concatenate([p["scale"] for p in pyr])
 
-        imgs_dev = [torch.as_tensor(np.ascontiguousarray(im, dtype=np.uint8), device=dev) for im in images]
+        imgs_dev = [im if torch.is_tensor(im) else torch.as_tensor(np.ascontiguousarray(im, dtype=np.uint8), device=dev)
+                    for im in images]
+        for t in imgs_dev:
+            if t.dtype != torch.uint8 or t.dim() != 2 or not t.is_contiguous() or t.device != dev:
+                raise ValueError("images must be contiguous 2-D uint8 arrays (mode 'L') on %s" % (dev,))
         img_ptrs = torch.tensor([t.data_ptr() for t in imgs_dev], dtype=torch.int64, device=dev)
         img_hw = torch.tensor([[t.shape[0], t.shape[1]] for t in imgs_dev], dtype=torch.int32, device=dev)
 
@@ -251,39 +330,75 @@ class FaceDetector(object):
         orig_idx = torch.arange(n0, dtype=torch.int32, device=dev)
         conf = torch.zeros(n0, dtype=torch.float64, device=dev)
         keep = torch.empty(n0, dtype=torch.uint8, device=dev)
+        alive = torch.ones(n0, dtype=torch.uint8, device=dev)              # windows not discarded by any stage so far
         src_index = torch.empty(n0, dtype=torch.int32, device=dev)
         count_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        counts_dev = torch.zeros(n_stages, dtype=torch.int64, device=dev)  # windows entering every stage, read once
         scratch = torch.empty(max(1, (n0 + 1023) // 1024), dtype=torch.int32, device=dev)
         sl = None
+        patches = None                                                    # (n, sw * sh) uint8, row-major
         n = n0
         disc_scores = {}
+        host_syncs = 0
         min_r = net_mins / 0.825
         max_r = net_maxs / 0.825
 
-        mark("pyramid+upload")
+        def compact():
+            """Order-preserving compaction of every per-window array by `alive`: the ONE kind of host round trip of the
+            stage loop (the survivor count sizes the next launches)."""
+            nonlocal coords, angles, img_idx, orig_idx, conf, sl, patches, alive, n, host_syncs
+            _lib.check(lib.hgsfa_compact_index_device(C.c_void_p(alive.data_ptr()), n, C.c_void_p(src_index.data_ptr()),
+                                                      C.c_void_p(count_dev.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                                      scratch.numel(), sp))
+            n_new = int(count_dev.item())
+            host_syncs += 1
+            if n_new == n:
+                return
+
+            def gather(t, row_bytes):
+                out = torch.empty((n_new,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+                if n_new:
+                    _lib.check(lib.hgsfa_gather_rows_device(C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                            C.c_void_p(src_index.data_ptr()), n_new, row_bytes, sp))
+                return out
+            coords = gather(coords, 32)
+            angles = gather(angles, 8)
+            img_idx = gather(img_idx, 4)
+            orig_idx = gather(orig_idx, 4)
+            conf = gather(conf, 8)
+            if sl is not None:
+                sl = gather(sl.contiguous(), sl.shape[1] * 4)
+            if patches is not None:
+                patches = gather(patches, patches.shape[1])
+            alive = torch.ones(n_new, dtype=torch.uint8, device=dev)
+            n = n_new
+
+        mark("pyramid+upload", "Window creation, and pre-computations")
         for k, full_type in enumerate(self.types):
-            counts[k] = n
             if n == 0:
-                continue
+                break
+            counts_dev[k] = alive[:n].sum()
             ntype, serial = full_type[:-1], int(full_type[-1])
             net, clf = self.networks[k], self.classifiers[k]
             if net is not None:
-                # patches are re-extracted from the current boxes: after a Disc stage the boxes are unchanged,
-                # so this equals the reference's reuse of the compacted subimages_arr (FaceDetectUpdated.py:674-682)
-                n_pad = (n + _lib.TILE - 1) // _lib.TILE * _lib.TILE
-                patches = torch.empty(n_pad * sw * sh, dtype=torch.uint8, device=dev)
-                _lib.check(lib.hgsfa_crop_extent_batch_device(
-                    C.c_void_p(img_ptrs.data_ptr()), C.c_void_p(img_hw.data_ptr()), C.c_void_p(img_idx.data_ptr()),
-                    C.c_void_p(coords.data_ptr()), C.c_void_p(angles.data_ptr()), n, sw, sh, self.interpolation,
-                    C.c_void_p(patches.data_ptr()), _lib.U8, _lib.TILED, sp))
-                mark("crop[%d]" % min(k, 1))
-                sl = net.execute_torch(patches, layout=_lib.TILED, n=n)
-                mark("flow[%d]" % min(k, 1))
+                # the reference re-extracts unless the previous stage was a Disc, whose compacted subimages_arr it keeps
+                # (FaceDetectUpdated.py:674-682); a Disc stage does not move boxes, so the kept patches are the same pixels
+                reuse = k > 0 and self.types[k - 1][:-1] == "Disc" and patches is not None and patches.shape[0] == n
+                if not reuse:
+                    patches = torch.empty((n, sw * sh), dtype=torch.uint8, device=dev)
+                    _lib.check(lib.hgsfa_crop_extent_batch_device(
+                        C.c_void_p(img_ptrs.data_ptr()), C.c_void_p(img_hw.data_ptr()), C.c_void_p(img_idx.data_ptr()),
+                        C.c_void_p(coords.data_ptr()), C.c_void_p(angles.data_ptr()), n, sw, sh, self.interpolation,
+                        C.c_void_p(patches.data_ptr()), _lib.U8, _lib.ROWMAJOR, sp))
+                mark("crop[%d]" % min(k, 1), "Extraction of subimages patches")
+                sl = net.execute_torch(patches)
+                mark("flow[%d]" % min(k, 1), "Feature extraction")
             elif sl is None:
                 raise ValueError("stage %s reuses features but none were computed" % full_type)
             reg = self._regress(clf, sl, n, sp)
+            mark("head[%d]" % min(k, 1), "Regression")
             if return_trace and ntype == "Disc":
-                disc_scores[full_type] = reg.cpu().numpy()
+                disc_scores[full_type] = (reg, alive.clone())
             params = np.array([net_Dx, net_Dy, net_Dang, rw, rh, min_r, max_r, self.cfg["tolerance_posxy_deviation"],
                                self.cfg["tolerance_scale_deviation"], self.cfg["tolerance_angle_deviation"], 0.825,
                                self.cut_offs[serial]], dtype=np.float64)
@@ -292,26 +407,17 @@ class FaceDetector(object):
                 C.c_void_p(reg.data_ptr()), C.c_void_p(orig_coords.data_ptr()), C.c_void_p(orig_angles.data_ptr()),
                 C.c_void_p(orig_idx.data_ptr()), C.c_void_p(patch_wh.data_ptr()), n, _lib.ptr(params),
                 C.c_void_p(keep.data_ptr()), C.c_void_p(conf.data_ptr()) if ntype == "Disc" else None, sp))
-            _lib.check(lib.hgsfa_compact_index_device(C.c_void_p(keep.data_ptr()), n, C.c_void_p(src_index.data_ptr()),
-                                                      C.c_void_p(count_dev.data_ptr()), C.c_void_p(scratch.data_ptr()),
-                                                      scratch.numel(), sp))
-            n_new = int(count_dev.item())          # the one host round trip of the stage
-            mark("head+update+compact[%d]" % min(k, 1))
-            if n_new < n:
-                def gather(t, row_bytes):
-                    out = torch.empty((n_new,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-                    if n_new:
-                        _lib.check(lib.hgsfa_gather_rows_device(C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()),
-                                                                C.c_void_p(src_index.data_ptr()), n_new, row_bytes, sp))
-                    return out
-                coords = gather(coords, 32)
-                angles = gather(angles, 8)
-                img_idx = gather(img_idx, 4)
-                orig_idx = gather(orig_idx, 4)
-                conf = gather(conf, 8)
-                sl = gather(sl.contiguous(), sl.shape[1] * 4)
-                n = n_new
-                mark("gather[%d]" % min(k, 1))
+            alive[:n] &= keep[:n]
+            # Windows are independent, so a discarded window may stay in the batch (its results are never read): the arrays
+            # are compacted -- the only host round trip -- where it pays, after a Disc stage while the batch is still
+            # large (the first Disc stage removes most windows); later stages run on the small remainder unsynchronised.
+            if ntype == "Disc" and n > self.lazy_threshold:
+                compact()
+            mark("update+compact[%d]" % min(k, 1), "Adjusted according to regression")
+        compact()                                                          # survivors of the face stages
+        counts = counts_dev.cpu().numpy()
+        if return_trace:
+            disc_scores = {name: r[a.bool()].cpu().numpy() for name, (r, a) in disc_scores.items()}
 
         # ---- survivors -> eyes -> detections (host arithmetic on dozens of rows, device compute for the eye flow) ----
         boxes = coords[:n].cpu().numpy()
@@ -347,13 +453,19 @@ class FaceDetector(object):
             n = len(boxes)
         else:
             eyes = approximate_eye_coordinates(boxes, ang) if n else np.zeros((0, 4))
-        mark("eyes")
+        mark("eyes", "Eye localization (patches, feature extraction, regression)")
         raw = np.concatenate([boxes, ang[:, None], eyes, cf[:, None]], axis=1) if n else np.zeros((0, 10))
         per_image_raw = [raw[im_of == k] for k in range(len(images))]
         result = [purge_detections(r) if len(r) else np.zeros((0, 10)) for r in per_image_raw]
-        mark("purge")
+        mark("purge", "Purgued repeated face detections")
         if prof is not None:
             self.last_profile = prof
+        if marks is not None:
+            # device time between consecutive marks, booked under the reference's Benchmark labels
+            torch.cuda.synchronize(dev)
+            for (_, e_prev), (label, e) in zip(marks[:-1], marks[1:]):
+                benchmark.add_task_ellapsed(label, e_prev.elapsed_time(e) * 1e-3)
         if return_trace:
-            return result, dict(stage_counts=counts, raw=per_image_raw, n_windows=n0, disc_scores=disc_scores)
+            return result, dict(stage_counts=counts, raw=per_image_raw, n_windows=n0, disc_scores=disc_scores,
+                                host_syncs=host_syncs)
         return result

@@ -388,6 +388,110 @@ __global__ void __launch_bounds__(256) crop_tiled_kernel(const uint8_t* img0, in
   }
 }
 
+// Row-major uint8 patches (what the fused flow front reads in place through its tensor map): the fast path of the detector.
+// CTA = CROP_RW windows, 256 threads.
+//   1. thread (window, axis) builds the NEAREST index table of its window in shared memory (Pillow's sequential double
+//      accumulation, as in crop_index_kernel) and resolves the window's image pointer / size / angle.
+//   2. a warp takes one window at a time; a lane produces 16 consecutive pixels of a row -- 16 independent byte
+//      gathers in flight (the image is L2 / L1 resident), packed with PRMT into ONE 16-byte store; a warp's stores cover
+//      512 contiguous bytes (8 patch rows).  Rotated / BILINEAR / BICUBIC windows take the generic per-pixel path.
+constexpr int CROP_RW = 32;
+__global__ void __launch_bounds__(256) crop_rows_u8_kernel(const uint8_t* img0, int H0, int W0, const double* __restrict__ boxes,
+                                                           const double* __restrict__ angles, int64_t n, int ow, int oh,
+                                                           int filter, ImageTable tab_img, uint8_t* __restrict__ dst) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  int* xs = reinterpret_cast<int*>(smem_raw);                 // [CROP_RW][ow]
+  int* ys = xs + CROP_RW * ow;                                // [CROP_RW][oh]
+  __shared__ const uint8_t* w_img[CROP_RW];
+  __shared__ int w_W[CROP_RW], w_H[CROP_RW];
+  __shared__ double w_ang[CROP_RW];
+  const int64_t w0 = int64_t(blockIdx.x) * CROP_RW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 2 * CROP_RW) {
+    const int wl = tid >> 1, axis = tid & 1;
+    const int64_t w = w0 + wl;
+    const int cnt = axis ? oh : ow;
+    int* tab = axis ? ys + wl * oh : xs + wl * ow;
+    int Hh = H0, Ww = W0;
+    const uint8_t* ip = img0;
+    if (w < n && tab_img.index) {
+      const int im = tab_img.index[w];
+      ip = tab_img.ptrs[im];
+      Hh = tab_img.hw[2 * im];
+      Ww = tab_img.hw[2 * im + 1];
+    }
+    if (axis == 0) {
+      w_img[wl] = ip;
+      w_W[wl] = Ww;
+      w_H[wl] = Hh;
+      w_ang[wl] = (w < n && angles) ? angles[w] : 0.0;
+    }
+    if (w < n) {
+      const double lo = boxes[w * 4 + axis], hi = boxes[w * 4 + 2 + axis];
+      const int size = axis ? Hh : Ww;
+      const double a = __ddiv_rn(__dsub_rn(hi, lo), double(cnt));
+      double xo = __dadd_rn(lo, __dmul_rn(a, 0.5));
+      for (int c = 0; c < cnt; ++c) {
+        int idx = -1;
+        if (!(xo < 0.0) && xo < double(size)) idx = int(xo);
+        tab[c] = idx;
+        xo = __dadd_rn(xo, a);
+      }
+    }
+  }
+  __syncthreads();
+  const int chunks_per_row = ow / 16, n_chunks = chunks_per_row * oh;
+  for (int wl = warp; wl < CROP_RW; wl += 8) {
+    const int64_t w = w0 + wl;
+    if (w >= n) break;
+    const uint8_t* img = w_img[wl];
+    const int W = w_W[wl], H = w_H[wl];
+    const double ang = w_ang[wl];
+    uint4* out = reinterpret_cast<uint4*>(dst + size_t(w) * ow * oh);
+    if (ang == 0.0 && filter == HGSFA_NEAREST) {
+      const int* xt = xs + wl * ow;
+      const int* yt = ys + wl * oh;
+      for (int ch = lane; ch < n_chunks; ch += 32) {
+        const int r = ch / chunks_per_row, c0 = (ch - r * chunks_per_row) * 16;
+        const int y = yt[r];
+        uint32_t px[16];
+        if (y >= 0) {
+          const uint8_t* row = img + size_t(y) * W;
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) {
+            const int4 x = *reinterpret_cast<const int4*>(xt + c0 + k);
+            px[k + 0] = x.x >= 0 ? uint32_t(__ldg(row + x.x)) : 0u;
+            px[k + 1] = x.y >= 0 ? uint32_t(__ldg(row + x.y)) : 0u;
+            px[k + 2] = x.z >= 0 ? uint32_t(__ldg(row + x.z)) : 0u;
+            px[k + 3] = x.w >= 0 ? uint32_t(__ldg(row + x.w)) : 0u;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) px[k] = 0u;
+        }
+        uint4 v;
+        v.x = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+        v.y = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+        v.z = px[8] | (px[9] << 8) | (px[10] << 16) | (px[11] << 24);
+        v.w = px[12] | (px[13] << 8) | (px[14] << 16) | (px[15] << 24);
+        out[ch] = v;
+      }
+    } else {
+      double cs = 1.0, sn = 0.0;
+      const double box[4] = {boxes[w * 4 + 0], boxes[w * 4 + 1], boxes[w * 4 + 2], boxes[w * 4 + 3]};
+      if (ang != 0.0) {
+        const double th = __ddiv_rn(__dmul_rn(-ang, 3.141592653589793), 180.0);   // delta_ang = -angle (face_analysis.py:781)
+        sincos(th, &sn, &cs);
+      }
+      uint8_t* o = dst + size_t(w) * ow * oh;
+      for (int p = lane; p < ow * oh; p += 32) {
+        const int r = p / ow, c = p - r * ow;
+        o[p] = sample_generic(img, W, H, box, cs, sn, ang != 0.0, ow, oh, c, r, filter);
+      }
+    }
+  }
+}
+
 // Per-patch contrast normalisation of TILED float patches, in place (cuicuilco's
 // "AgeContrastEnhancement_Avg_Std" as defined by oracle/crop.py: v = x / 255;
 // y = (v - mean(v)) / (std(v) + 1e-8) * obj_std + obj_avg).  A lane owns one window: every load of a
@@ -455,6 +559,20 @@ int crop_launch(const uint8_t* d_img, int H, int W, ImageTable tab, const double
   const size_t stage_bytes = (size_t(ow) * (TILE_W + 4) + 15) & ~size_t(15);
   const size_t fused_smem = stage_bytes + size_t(TILE_W) * (ow + 1 + oh + 1) * sizeof(int);
   const bool fused = out_layout == HGSFA_TILED && fused_smem <= size_t(160) * 1024;
+  // row-major uint8 patches with tables that fit in shared memory: the detector's path (crop_rows_u8_kernel)
+  const size_t rows_smem = size_t(CROP_RW) * (ow + oh) * sizeof(int);
+  if (out_layout == HGSFA_ROWMAJOR && out_dtype == HGSFA_U8 && ow % 16 == 0 && rows_smem <= size_t(96) * 1024 &&
+      (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+    static thread_local bool rows_attr[16] = {};
+    if (!rows_attr[device & 15]) {
+      HG_CUDA(cudaFuncSetAttribute(crop_rows_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      rows_attr[device & 15] = true;
+    }
+    crop_rows_u8_kernel<<<(unsigned)ceil_div(n, CROP_RW), 256, rows_smem, st>>>(d_img, H, W, d_boxes, d_angles, n, ow, oh, filter, tab,
+                                                                              static_cast<uint8_t*>(d_out));
+    HG_CUDA(cudaGetLastError());
+    return 0;
+  }
   int* xtab = nullptr;
   int* ytab = nullptr;
   if (!fused) {

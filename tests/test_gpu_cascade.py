@@ -8,6 +8,7 @@ import pytest
 import cascade_models as cm
 from oracle import cascade as ocascade
 from oracle import controller as octl
+from oracle import nodes as onodes
 
 pytestmark = pytest.mark.gpu
 CUT = [0.99, 0.95, 0.85, 0.8, 0.7, 0.6, 0.5, 0.45, 0.10, 0.6]   # like --last_cut_off_face (FaceDetectUpdated.py:434-438)
@@ -227,3 +228,180 @@ def test_eye_stage_discards_far_eyes():
     # pure float64 oracle: a window within the numerical tolerance of a threshold may survive on one side only
     assert abs(len(trace["raw"][0]) - len(tr["raw"])) <= 2
     assert len(trace["raw"][0]) <= trace["stage_counts"][-1]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE configs on the U11L_64 model set (the network the benchmark times), both engines
+# ------------------------------------------------------------------------------------------------------------
+_ORACLE_RUNS = {}
+
+
+def _u11l_detector(engine, monkeypatch):
+    from pyfaceanalysis_b200 import plan
+    from pyfaceanalysis_b200.cascade import FaceDetector
+    monkeypatch.setattr(plan, "ENGINE", engine)
+    m = cm.cached_models(spec="U11L_64")
+    nets, clfs = _gpu_models(m)
+    face_nets = [g for g in nets[:m["num_face_stages"]] if g is not None]
+    assert all(g.fused_front == (engine == "auto") for g in face_nets)      # uint8 face stages take the fused front
+    det = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=CUT, header_eye=m["header_eye"])
+    return m, det, nets, clfs
+
+
+def _oracle_run(key, img, m, smallest_face):
+    """The pure float64 oracle loop (slow: numpy flows), shared by the engine parametrisations of a test."""
+    if key not in _ORACLE_RUNS:
+        _ORACLE_RUNS[key] = ocascade.detect_image(img, m["header"], m["network_types"], m["networks"], m["classifiers"],
+                                                  smallest_face, m["num_face_stages"], cut_offs_face=CUT,
+                                                  eye_header=m["header_eye"])
+    return _ORACLE_RUNS[key]
+
+
+def _hybrid_run(img, m, nets, clfs, smallest_face, noise=0.0, seed=0):
+    """The oracle's statement-by-statement loop driven with the GPU flow and head (optionally with features perturbed
+    by `noise` x per-feature std): isolates batching + controller + compaction, and probes threshold sensitivity."""
+    gpu_flow = {id(f): g for f, g in zip(m["networks"], nets) if f is not None}
+    gpu_head = {id(c): g for c, g in zip(m["classifiers"], clfs) if c is not None}
+    rng = np.random.default_rng(seed)
+
+    def flow_execute(f, x):
+        y = gpu_flow[id(f)].execute(x.astype(np.uint8) if np.array_equal(x, np.rint(x)) else x.astype(np.float32),
+                                    out_dtype=np.float32).astype(np.float64)
+        if noise:
+            y = (y + rng.standard_normal(y.shape) * noise * f._train_output_std).astype(np.float32).astype(np.float64)
+        return y
+    return ocascade.detect_image(img, m["header"], m["network_types"], m["networks"], m["classifiers"], smallest_face,
+                                 m["num_face_stages"], cut_offs_face=CUT, eye_header=m["header_eye"], flow_execute=flow_execute,
+                                 regression=lambda c, x, lab: gpu_head[id(c)].regression(x.astype(np.float32), lab))
+
+
+def _check_config(img_host, img_for_detect, m, det, nets, clfs, smallest_face, n_windows, oracle_key, level, n_perturbed=2,
+                  hybrid=True):
+    """(1) batched device cascade == oracle loop driven with the GPU flow / head, exactly;
+    (2) against the pure float64 oracle: the first round of stages (before any re-crop of regressed boxes) has equal
+        counts; later the synthetic heads are chaotic -- the float64 oracle itself changes its survivor counts and moves a
+        third of its final boxes by more than a pixel when its features are perturbed by 1e-5 x std, a hundredth of the
+        tolerance (windows scoring within a hair of a Disc cut-off, multi-modal class posteriors) -- so the check is the
+        north star's "identical except for windows within the tolerance of a threshold": the oracle's counts and
+        detection list must lie inside what the GPU cascade itself spans when its features are perturbed at the
+        engine's error level `level` x std."""
+    got, trace = det.detect([img_for_detect], smallest_face=smallest_face, return_trace=True)
+    assert trace["n_windows"] == n_windows
+    purged, tr = _oracle_run(oracle_key, img_host, m, smallest_face)
+    pairs, only_gpu, only_ref = _match_rows(trace["raw"][0], tr["raw"])
+    print("stage counts gpu", trace["stage_counts"].tolist(), "\n             oracle", tr["stage_counts"].tolist(),
+          "\n  detections gpu %d oracle %d, unmatched within 1 px %d / %d" % (len(trace["raw"][0]), len(tr["raw"]), only_gpu, only_ref))
+    assert trace["stage_counts"][:6].tolist() == tr["stage_counts"][:6].tolist()
+    margin = np.maximum(3, np.ceil(0.05 * tr["stage_counts"])).astype(np.int64)
+    if not hybrid:
+        assert (np.abs(trace["stage_counts"] - tr["stage_counts"]) <= 2 * margin).all()
+        return trace, tr
+    hyb, trh = _hybrid_run(img_host, m, nets, clfs, smallest_face)
+    assert np.array_equal(trace["stage_counts"], trh["stage_counts"])
+    assert trace["raw"][0].shape == trh["raw"].shape
+    assert np.allclose(trace["raw"][0][:, [0, 1, 2, 3, 4, 9]], trh["raw"][:, [0, 1, 2, 3, 4, 9]], rtol=0, atol=1e-9)
+    assert np.allclose(trace["raw"][0], trh["raw"], rtol=0, atol=1e-4) and np.allclose(got[0], hyb, rtol=0, atol=1e-4)
+    band, self_unmatched = [trace["stage_counts"]], [0]
+    for seed in range(n_perturbed):
+        _, trp = _hybrid_run(img_host, m, nets, clfs, smallest_face, noise=level, seed=seed)
+        band.append(trp["stage_counts"])
+        self_unmatched.append(max(_match_rows(trp["raw"], trh["raw"])[1:]))
+    lo, hi = np.min(band, axis=0), np.max(band, axis=0)
+    print("  gpu band at %.0e x std" % level, lo.tolist(), hi.tolist(), "perturbed gpu vs gpu unmatched", self_unmatched)
+    assert ((tr["stage_counts"] >= lo - margin) & (tr["stage_counts"] <= hi + margin)).all()
+    if n_perturbed:
+        assert max(only_gpu, only_ref) <= max(self_unmatched) + max(3, int(0.1 * len(tr["raw"])))
+        assert abs(len(got[0]) - len(purged)) <= max(self_unmatched) + 3
+    return trace, tr
+
+
+@pytest.mark.parametrize("engine", ["auto", "ffma"])
+def test_config1_tns_group_real_image(engine, monkeypatch):
+    """BASELINE configs[0]: sample_images/TNS-Group.jpg (README.md:43), --smallest_face=0.1, prescaled NEAREST to
+    1000 x 750 (fixture made by tools/make_golden.py with the reference's own Pillow calls) -> 10 scales, 1 308 windows,
+    17 face stages + eye stage + purge.  Oracle = the statement-by-statement float64 loop, run live and pinned by
+    tests/golden/cascade_golden.json."""
+    import json
+    import os
+    from PIL import Image
+    from conftest import GOLDEN
+    img = np.ascontiguousarray(Image.open(os.path.join(GOLDEN, "tns_group_1000x750.png")))
+    assert img.shape == (750, 1000) and img.dtype == np.uint8
+    with open(os.path.join(GOLDEN, "cascade_golden.json")) as f:
+        gold = json.load(f)
+    m, det, nets, clfs = _u11l_detector(engine, monkeypatch)
+    trace, tr = _check_config(img, img, m, det, nets, clfs, 0.1, 1308, "tns", 1e-5 if engine == "ffma" else 1e-4,
+                              n_perturbed=2 if engine == "auto" else 0)
+    assert tr["stage_counts"].tolist() == gold["stage_counts"]                       # the oracle is pinned on this fixture
+    assert np.allclose(tr["raw"], np.asarray(gold["raw"]).reshape(-1, 10), rtol=0, atol=1e-5)
+    assert trace["host_syncs"] <= 3                      # one compaction after Disc1 (none here: 1 308 windows), one at the end
+
+
+@pytest.mark.parametrize("engine", ["auto"])
+def test_config3_fhd_image_with_device_prescale(engine, monkeypatch):
+    """One image of BASELINE configs[2]: 1920 x 1080, smallest_face 0.05, NEAREST prescale to 1000 x 562 ON THE DEVICE
+    (bit-exact against Pillow's resize, FaceDetectUpdated.py:551-559) -> 12 scales, 7 452 windows through the cascade;
+    the prescaled image stays on the device (no upload in detect)."""
+    from PIL import Image
+    rng = np.random.default_rng(77)
+    faces = [(rng.uniform(200, 1700), rng.uniform(200, 900), rng.uniform(90, 300), rng.uniform(-10, 10)) for _ in range(5)]
+    full = cm.render_scene(1080, 1920, faces, 4242)
+    m, det, nets, clfs = _u11l_detector(engine, monkeypatch)
+    small = det.prescale([full])[0]
+    ref_small = np.ascontiguousarray(Image.fromarray(full, "L").resize((1000, 562), Image.NEAREST))
+    assert tuple(small.shape) == (562, 1000) and np.array_equal(small.cpu().numpy(), ref_small)
+    # (the oracle loop costs ~1.5 min of host time per run at this size: one pure-oracle run, no perturbed re-runs)
+    _check_config(ref_small, small, m, det, nets, clfs, 0.05, 7452, "fhd", 1e-4, n_perturbed=0, hybrid=False)
+    # several images of one size are prescaled by one launch
+    many = det.prescale([full, full[::-1].copy(), full])
+    assert np.array_equal(many[0].cpu().numpy(), ref_small) and np.array_equal(many[2].cpu().numpy(), ref_small)
+    assert np.array_equal(many[1].cpu().numpy(), np.asarray(Image.fromarray(full[::-1].copy(), "L").resize((1000, 562), Image.NEAREST)))
+
+
+def test_lazy_compaction_is_invisible(monkeypatch):
+    """Discarded windows may ride along until the next compaction (cascade.py): forcing a compaction after every Disc
+    stage, or none before the end, gives the same detections, counts and order."""
+    from pyfaceanalysis_b200.cascade import FaceDetector
+    m = cm.cached_models()
+    nets, clfs = _gpu_models(m)
+    images = [cm.test_scene(seed)[0] for seed in (5, 8)]
+    outs = []
+    for thr in (0, 32768, 1 << 40):
+        det = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=CUT, header_eye=m["header_eye"],
+                           lazy_threshold=thr)
+        got, trace = det.detect(images, smallest_face=0.2, return_trace=True)
+        outs.append((got, trace))
+    assert outs[0][1]["host_syncs"] > outs[2][1]["host_syncs"] == 1
+    for got, trace in outs[1:]:
+        assert np.array_equal(trace["stage_counts"], outs[0][1]["stage_counts"])
+        for a, b in zip(got, outs[0][0]):
+            assert np.array_equal(a, b)
+
+
+def test_benchmark_labels_and_result_lines():
+    """benchmark= receives device times under the reference's labels (FaceDetectUpdated.py:691,711,724,760); the text
+    writer reproduces the result line format (FaceDetectUpdated.py:1258-1278)."""
+    from pyfaceanalysis_b200.cascade import FaceDetector, format_detections
+    m = cm.cached_models()
+    nets, clfs = _gpu_models(m)
+    det = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=CUT, header_eye=m["header_eye"])
+
+    class Bench(object):                      # the add_task_ellapsed surface of the reference's benchmarking.Benchmark
+        def __init__(self):
+            self.tasks = {}
+
+        def add_task_ellapsed(self, task_label, ellapsed_time, reference=None):
+            t, k = self.tasks.get(task_label, (0.0, 0))
+            self.tasks[task_label] = (t + ellapsed_time, k + 1)
+    b = Bench()
+    got = det.detect([cm.test_scene(5)[0]], smallest_face=0.2, benchmark=b)
+    for label in ("Extraction of subimages patches", "Feature extraction", "Regression", "Adjusted according to regression",
+                  "Window creation, and pre-computations", "Purgued repeated face detections"):
+        assert label in b.tasks and b.tasks[label][0] > 0.0, label
+    assert b.tasks["Regression"][1] == 17 and b.tasks["Feature extraction"][1] == 8
+    text = format_detections(got[0])
+    assert text.count("\n") == len(got[0])
+    if len(got[0]):
+        r = got[0][0]
+        first = text.split(" \n")[0].split(", ")
+        assert len(first) == 9 and int(first[0]) == int(np.round(r[0])) and float(first[4]) == pytest.approx(r[4], abs=1e-6)

@@ -9,6 +9,8 @@ container, where /root/reference exists; the GPU box only ever sees the fixtures
                     image for random, overhanging and adversarial boxes
   grid_golden.json: window counts per scale for the BASELINE.md image sizes, from the oracle grid
                     (which is the reference arithmetic of face_analysis.py:575-669)
+  tns_group_1000x750.png : BASELINE config 1 input -- sample_images/TNS-Group.jpg (README.md:43) opened in mode 'L' and
+                    prescaled exactly like FaceDetectUpdated.py:551-559 (Pillow resize NEAREST to 1000 x 750)
 """
 import json
 import os
@@ -114,8 +116,19 @@ def grid_golden(pipe):
     return cases
 
 
+def tns_image():
+    from PIL import Image
+    im = Image.open(os.path.join(REF, "sample_images", "TNS-Group.jpg")).convert("L")
+    factor = max(im.size[0] * 1.0 / 1000, im.size[1] * 1.0 / 1000)
+    size = (int(im.size[0] / factor), int(im.size[1] / factor))
+    small = im.resize(size, Image.NEAREST)
+    small.save(os.path.join(OUT, "tns_group_1000x750.png"), optimize=True)
+    return im.size, small.size
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    print("TNS-Group:", tns_image())
     names = classifiers()
     print("classifiers:", len(names))
     pipe = pipeline()
