@@ -139,6 +139,18 @@ int hgsfa_crop_extent_batch_device(const uint8_t* const* d_img_ptrs, const int32
 int hgsfa_contrast_avg_std_device(float* d_patches_tiled, int64_t n, int64_t dim, double obj_avg,
                                   double obj_std, void* stream);
 
+/* Age-stage crop of n faces: replaces face_normalization_tools.normalize_image (face_normalization_tools.py:111-329,
+ * called at face_analysis.py:1212) followed by the 96 x 96 sub-sampling of load_image_data_monoprocessor
+ * (face_analysis.py:1230-1246) -- integer crop -> BICUBIC rotation -> BICUBIC EXTENT to 256 x 260 -> NEAREST
+ * sub-sampling -- evaluated per output sample without materialising the intermediate images.
+ * d_params: n x 16 doubles per face (pyfaceanalysis_b200/normalize.py: crop origin x, y, crop width, height, rotate
+ * flag, rotation matrix a0..a5, EXTENT affine xs, x0, ys, y0); d_xtab / d_ytab: ow / oh NEAREST source indices into the
+ * 256 x 260 image (-1 = outside).  Output: TILED float32 patches with values 0..255 (feed
+ * hgsfa_contrast_avg_std_device, then the age flow). */
+int hgsfa_age_crop_device(const uint8_t* const* d_img_ptrs, const int32_t* d_img_hw, const int32_t* d_img_index,
+                          const double* d_params, int64_t n, const int32_t* d_xtab, const int32_t* d_ytab, int ow,
+                          int oh, float* d_out_tiled, void* stream);
+
 /* row-major <-> tiled conversion of a window matrix on the device (u8 or f32 elements) */
 int hgsfa_tile_windows_device(const void* d_src, int dtype, int64_t n, int64_t dim, int64_t ld,
                               void* d_dst_tiled, int dst_dtype, void* stream);

@@ -41,6 +41,7 @@ SYMBOLS = [
     ("hgsfa_crop_extent_device", _int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int, _int, _vp, _int, _int, _vp]),
     ("hgsfa_crop_extent_batch_device", _int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _int, _int, _vp]),
     ("hgsfa_contrast_avg_std_device", _int, [_vp, _i64, _i64, C.c_double, C.c_double, _vp]),
+    ("hgsfa_age_crop_device", _int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp]),
     ("hgsfa_tile_windows_device", _int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _vp]),
     ("hgsfa_gauss_create", _int, [_vp, _vp, _vp, _vp, _int, _int, _int, C.POINTER(_vp)]),
     ("hgsfa_gauss_destroy", _int, [_vp]),

@@ -131,7 +131,7 @@ class FaceDetector(object):
     """
 
     def __init__(self, header_net, network_types, networks, classifiers, num_face_stages=None,
-                 cut_offs_face=None, interpolation=_lib.NEAREST, device=0, header_eye=None, **overrides):
+                 cut_offs_face=None, interpolation=_lib.NEAREST, device=0, header_eye=None, attributes=None, **overrides):
         import torch
         self.torch = torch
         self.header = tuple(header_net)
@@ -148,6 +148,8 @@ class FaceDetector(object):
         if self.networks and self.networks[0] is None:
             raise ValueError("the first stage needs a network")
         self._labels = {}
+        # age / race / gender stage (attributes.AttributeEstimator built from the last three network / classifier pairs)
+        self.attributes = attributes
         # windows above which a Disc stage is followed by a compaction (one host round trip); below it discarded windows
         # simply ride along
         self.lazy_threshold = int(self.cfg.get("lazy_threshold", 32768))
@@ -264,19 +266,22 @@ class FaceDetector(object):
                     out[k] = dst[j]
         return out
 
-    def detect(self, images, smallest_face=0.2, return_trace=False, benchmark=None):
+    def detect(self, images, smallest_face=0.2, return_trace=False, benchmark=None, estimate_attributes=False):
         """images: list of 2-D uint8 arrays (the reference's mode-'L' image, already prescaled) or CUDA uint8 tensors
         (e.g. from ``prescale``).  Returns a list (one entry per image) of (M,10) float64 detection arrays after the
         purge; with ``return_trace`` also a dict with the per-stage window counts and the un-purged detections.
         ``benchmark``: an object with the reference's ``Benchmark.add_task_ellapsed(label, seconds)``
         (``benchmarking.py:39``); it receives the device time of every phase under the reference's labels
-        (``FaceDetectUpdated.py:691,711,724,760``), summed over the stages of the batch."""
+        (``FaceDetectUpdated.py:691,711,724,760``), summed over the stages of the batch.
+        ``estimate_attributes`` (needs ``attributes=`` at construction): also run the age / race / gender stage on the
+        purged detections (``FaceDetectUpdated.py:1187`` -> ``estimate_age_race_gender``); the per-image dicts come back
+        as a second return value, or as ``trace["attributes"]`` with ``return_trace``."""
         # the detector's device becomes current for the call: torch allocations, the stream looked up below and
         # every kernel launch then agree, whatever device the calling thread had selected
         with self.torch.cuda.device(self.dev):
-            return self._detect(images, smallest_face, return_trace, benchmark)
+            return self._detect(images, smallest_face, return_trace, benchmark, estimate_attributes)
 
-    def _detect(self, images, smallest_face, return_trace, benchmark):
+    def _detect(self, images, smallest_face, return_trace, benchmark, estimate_attributes=False):
         torch = self.torch
         lib = _lib.load()
         dev = self.dev
@@ -458,6 +463,12 @@ class FaceDetector(object):
         per_image_raw = [raw[im_of == k] for k in range(len(images))]
         result = [purge_detections(r) if len(r) else np.zeros((0, 10)) for r in per_image_raw]
         mark("purge", "Purgued repeated face detections")
+        attrs = None
+        if estimate_attributes:
+            if self.attributes is None:
+                raise ValueError("estimate_attributes needs FaceDetector(..., attributes=AttributeEstimator(...))")
+            attrs = self.attributes.estimate_detections(imgs_dev, result)
+            mark("attributes", "Age/race/gender: normalized image, image array, feature extraction, regressions")
         if prof is not None:
             self.last_profile = prof
         if marks is not None:
@@ -467,5 +478,5 @@ class FaceDetector(object):
                 benchmark.add_task_ellapsed(label, e_prev.elapsed_time(e) * 1e-3)
         if return_trace:
             return result, dict(stage_counts=counts, raw=per_image_raw, n_windows=n0, disc_scores=disc_scores,
-                                host_syncs=host_syncs)
-        return result
+                                host_syncs=host_syncs, attributes=attrs)
+        return (result, attrs) if estimate_attributes else result

@@ -492,6 +492,99 @@ __global__ void __launch_bounds__(256) crop_rows_u8_kernel(const uint8_t* img0, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Age-stage crop (reference normalize_image, face_normalization_tools.py:274-324, + the 96 x 96 sub-sampling of
+// face_analysis.py:1230-1246): integer crop around the rotation centre -> BICUBIC rotation -> BICUBIC EXTENT to
+// 256 x 260 -> NEAREST sub-sampling, each step a uint8 image in the reference.  Here one thread evaluates one output
+// sample through the whole chain: the pixel of the 256 x 260 image it needs is a bicubic over 4 x 4 pixels of the
+// rotated image, each of which is a bicubic over 4 x 4 pixels of the (virtual) crop -- same double arithmetic, same
+// clamping, same truncation to uint8 at every level as Pillow (pinned: tests/test_oracle_normalize.py), no
+// intermediate image in memory.  params per face (pyfaceanalysis_b200/normalize.py): crop origin x, y, crop width,
+// height, rotate flag (0 copy, 1 affine, 2 rotate-180), Pillow's rotation matrix a0..a5, EXTENT affine xs, x0, ys, y0.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int AGE_PARAMS = 16;
+
+struct CropImg {      // virtual uint8 image: the source image shifted by the integer crop origin, zero outside
+  const uint8_t* img;
+  int W, H, ox, oy;
+  __device__ __forceinline__ double operator()(int x, int y) const {
+    const int sx = x + ox, sy = y + oy;
+    return (sx >= 0 && sx < W && sy >= 0 && sy < H) ? double(img[size_t(sy) * W + sx]) : 0.0;
+  }
+};
+
+// Pillow bicubic_filter8 over a virtual image `px` of size (W, H); returns -1 where Pillow's filter rejects the point
+template <typename PX>
+__device__ __forceinline__ int bicubic_virtual(const PX& px, int W, int H, double xin, double yin) {
+  if (!(xin >= 0.0 && xin < double(W) && yin >= 0.0 && yin < double(H))) return -1;
+  const double xs = __dsub_rn(xin, 0.5), ys = __dsub_rn(yin, 0.5);
+  const double xf = floor(xs), yf = floor(ys);
+  const double dx = __dsub_rn(xs, xf), dy = __dsub_rn(ys, yf);
+  const int x = int(xf) - 1, y = int(yf) - 1;
+  int xc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) xc[k] = min(max(x + k, 0), W - 1);
+  double v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int yy = (k == 0) ? min(max(y, 0), H - 1) : y + k;
+    if (k == 0 || (yy >= 0 && yy < H)) v[k] = bicubic_poly(px(xc[0], yy), px(xc[1], yy), px(xc[2], yy), px(xc[3], yy), dx);
+    else v[k] = v[k - 1];
+  }
+  const double r = bicubic_poly(v[0], v[1], v[2], v[3], dy);
+  if (r <= 0.0) return 0;
+  if (r >= 255.0) return 255;
+  return int(uint8_t(r));
+}
+
+struct RotImg {       // virtual uint8 image: Pillow's rotate(angle, BICUBIC) of the crop (same size, zero fill)
+  CropImg crop;
+  int W, H, mode;
+  double a0, a1, a2, a3, a4, a5;
+  __device__ __forceinline__ double operator()(int x, int y) const {
+    if (mode == 0) return crop(x, y);
+    if (mode == 2) return crop(W - 1 - x, H - 1 - y);
+    const double xin = double(x) + 0.5, yin = double(y) + 0.5;
+    const double X = __dadd_rn(__dadd_rn(__dmul_rn(a0, xin), __dmul_rn(a1, yin)), a2);
+    const double Y = __dadd_rn(__dadd_rn(__dmul_rn(a3, xin), __dmul_rn(a4, yin)), a5);
+    const int v = bicubic_virtual(crop, W, H, X, Y);
+    return v < 0 ? 0.0 : double(v);
+  }
+};
+
+__global__ void __launch_bounds__(256) age_crop_kernel(ImageTable tab_img, const double* __restrict__ params, int64_t n,
+                                                       const int* __restrict__ xtab, const int* __restrict__ ytab, int ow, int oh,
+                                                       int mid_w, int mid_h, float* __restrict__ dst) {
+  const int64_t face = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (face >= n || p >= ow * oh) return;
+  const double* q = params + face * AGE_PARAMS;
+  const int im = tab_img.index[face];
+  RotImg rot;
+  rot.crop.img = tab_img.ptrs[im];
+  rot.crop.H = tab_img.hw[2 * im];
+  rot.crop.W = tab_img.hw[2 * im + 1];
+  rot.crop.ox = int(q[0]);
+  rot.crop.oy = int(q[1]);
+  rot.W = int(q[2]);
+  rot.H = int(q[3]);
+  rot.mode = int(q[4]);
+  rot.a0 = q[5]; rot.a1 = q[6]; rot.a2 = q[7]; rot.a3 = q[8]; rot.a4 = q[9]; rot.a5 = q[10];
+  const int r = p / ow, c = p - r * ow;
+  const int xi = xtab[c], yi = ytab[r];
+  float v = 0.f;
+  if (xi >= 0 && yi >= 0) {
+    // pixel (xi, yi) of the normalised image: EXTENT as the affine (xs, 0, x0, 0, ys, y0) evaluated like affine_transform
+    const double xin = double(xi) + 0.5, yin = double(yi) + 0.5;
+    const double X = __dadd_rn(__dadd_rn(__dmul_rn(q[11], xin), __dmul_rn(0.0, yin)), q[12]);
+    const double Y = __dadd_rn(__dadd_rn(__dmul_rn(0.0, xin), __dmul_rn(q[13], yin)), q[14]);
+    const int s = bicubic_virtual(rot, rot.W, rot.H, X, Y);
+    v = s < 0 ? 0.f : float(s);
+  }
+  (void)mid_w; (void)mid_h;
+  dst[(size_t(face / TILE_W) * ow * oh + p) * TILE_W + (face % TILE_W)] = v;       // window-minor tiles, like the eye patches
+}
+
 // Per-patch contrast normalisation of TILED float patches, in place (cuicuilco's
 // "AgeContrastEnhancement_Avg_Std" as defined by oracle/crop.py: v = x / 255;
 // y = (v - mean(v)) / (std(v) + 1e-8) * obj_std + obj_avg).  A lane owns one window: every load of a
@@ -651,6 +744,22 @@ extern "C" int hgsfa_contrast_avg_std_device(float* d_patches_tiled, int64_t n, 
   HG_CHECK(guard.ok, "hgsfa_contrast_avg_std: cannot select device %d", guard.device);
   contrast_avg_std_kernel<<<(unsigned)ceil_div(n, TILE_W), TILE_W, 0, static_cast<cudaStream_t>(stream)>>>(
       d_patches_tiled, n, dim, obj_avg, obj_std);
+  HG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hgsfa_age_crop_device(const uint8_t* const* d_img_ptrs, const int32_t* d_img_hw, const int32_t* d_img_index,
+                                     const double* d_params, int64_t n, const int32_t* d_xtab, const int32_t* d_ytab, int ow,
+                                     int oh, float* d_out_tiled, void* stream) {
+  HG_CHECK(n >= 0 && ow > 0 && oh > 0, "hgsfa_age_crop: bad shape n=%lld ow=%d oh=%d", (long long)n, ow, oh);
+  if (n == 0) return 0;
+  HG_CHECK(d_img_ptrs && d_img_hw && d_img_index && d_params && d_xtab && d_ytab && d_out_tiled, "hgsfa_age_crop: null buffer");
+  HG_CHECK(n <= 65535, "hgsfa_age_crop: %lld faces in one call (max 65535)", (long long)n);
+  PtrDeviceGuard guard(d_out_tiled);
+  HG_CHECK(guard.ok, "hgsfa_age_crop: cannot select device %d", guard.device);
+  dim3 grid((unsigned)ceil_div(int64_t(ow) * oh, 256), (unsigned)n);
+  age_crop_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(ImageTable{d_img_ptrs, d_img_hw, d_img_index}, d_params, n,
+                                                                      d_xtab, d_ytab, ow, oh, 256, 260, d_out_tiled);
   HG_CUDA(cudaGetLastError());
   return 0;
 }

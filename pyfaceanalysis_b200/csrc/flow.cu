@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -602,18 +603,33 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
     if (op.tc) max_tc = std::max(max_tc, std::max(op.tc_smem[0], op.tc_smem[1]));
     else max_smem = std::max(max_smem, std::max(op.smem_bytes[0], op.smem_bytes[1]));
   }
-  if (max_tc > 0 &&
-      (cudaFuncSetAttribute(layer_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess ||
-       cudaFuncSetAttribute(layer_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess))
-    return plan_fail(pl, "cannot reserve %zu bytes of dynamic shared memory for the tensor-core kernel", max_tc);
-  cudaError_t es[4] = {
-      cudaFuncSetAttribute(layer_kernel<uint8_t, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
-      cudaFuncSetAttribute(layer_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
-      cudaFuncSetAttribute(layer_kernel<uint8_t, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
-      cudaFuncSetAttribute(layer_kernel<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem)};
-  for (cudaError_t e : es)
-    if (e != cudaSuccess)
-      return plan_fail(pl, "cannot reserve %zu bytes of dynamic shared memory: %s", max_smem, cudaGetErrorString(e));
+  // The dynamic shared-memory limit of a kernel is per device and shared by every plan of the process: it only ever
+  // grows (a plan created later with smaller layers must not shrink it under the feet of an earlier plan -- that
+  // made the earlier plan's launches fail with "invalid argument").
+  {
+    static std::mutex mu;
+    static size_t dev_max_tc[64] = {}, dev_max_smem[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur_tc = dev_max_tc[device & 63];
+    size_t& cur_smem = dev_max_smem[device & 63];
+    if (max_tc > cur_tc) {
+      if (cudaFuncSetAttribute(layer_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess ||
+          cudaFuncSetAttribute(layer_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess)
+        return plan_fail(pl, "cannot reserve %zu bytes of dynamic shared memory for the tensor-core kernel", max_tc);
+      cur_tc = max_tc;
+    }
+    if (max_smem > cur_smem) {
+      cudaError_t es[4] = {
+          cudaFuncSetAttribute(layer_kernel<uint8_t, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
+          cudaFuncSetAttribute(layer_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
+          cudaFuncSetAttribute(layer_kernel<uint8_t, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem),
+          cudaFuncSetAttribute(layer_kernel<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem)};
+      for (cudaError_t e : es)
+        if (e != cudaSuccess)
+          return plan_fail(pl, "cannot reserve %zu bytes of dynamic shared memory: %s", max_smem, cudaGetErrorString(e));
+      cur_smem = max_smem;
+    }
+  }
   {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) pl->sm_count = prop.multiProcessorCount;

@@ -273,3 +273,16 @@ def test_attribute_estimator(u11l96_flow, classifiers):
     assert [r for r, k in zip(gender, ok) if k] == [r for r, k in zip(map_real_gender_labels_to_strings(g_ref), ok) if k]
     assert len(est.estimate(np.zeros((0, 9216)))[0]) == 0
     g.close()
+
+
+def test_plan_creation_order_does_not_matter(u11l96_flow, tiny_flow):
+    """The dynamic shared-memory limit of the layer kernels is per device, shared by all plans: a small plan created
+    after a large one must not shrink it (regression: the large plan's launches failed with 'invalid argument')."""
+    from pyfaceanalysis_b200 import GpuFlow, synthetic
+    big = GpuFlow(u11l96_flow)
+    small = GpuFlow(tiny_flow)
+    x = synthetic.synthetic_patches(130, (96, 96), 3).astype(np.float32)
+    y = big.execute(x)
+    assert np.isfinite(y).all() and small.execute(synthetic.synthetic_patches(5, (16, 16), 1)).shape == (5, 16)
+    big.close()
+    small.close()
