@@ -104,6 +104,8 @@ def _roofline(op_stats, steps, n, fl, kernel_ms_last, peaks, fp32_peak, fp32_src
     ceilings = {
         "front": ("hgsfa::front_kernel (layers 0-2 fused, lane-resident; tcgen05 kind::f16)", "tensor", bf16 / 3.0,
                   bf16_txt + " / 3 (2-piece FP16 split = 3 MMAs per algorithmic block)"),
+        "f16": ("hgsfa::back_kernel (one layer per launch, lane-resident; tcgen05 kind::f16)", "tensor", bf16 / 3.0,
+                bf16_txt + " / 3 (2-piece FP16 split = 3 MMAs per algorithmic block)"),
         "tc": ("hgsfa::layer_tc_kernel (tcgen05 kind::tf32)", "tensor", bf16 / 6.0,
                bf16_txt + " / 6 (TF32 = bf16 / 2; 3xTF32 split = 3 MMAs per algorithmic block)"),
         "ffma": ("hgsfa::layer_kernel (packed FP32 FMA)", "fp32", fp32_peak, fp32_src)}

@@ -15,6 +15,7 @@
 // run once per back_chunk windows so that every launch still fills the 148 SMs.
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -22,6 +23,8 @@
 #include "common.cuh"
 #include "layer.cuh"
 #include "layer_tc.cuh"
+#include <cuda_fp16.h>
+
 #include "front_api.h"
 
 namespace hgsfa {
@@ -134,6 +137,8 @@ struct OpHost {
   bool tc;               // runs on the tensor cores (layer_tc.cuh) instead of the FFMA kernel
   TcOpDev tcd;
   size_t tc_smem[2];
+  bool back;             // float inputs also run on the single-layer FP16-split kernel (back_tc.cuh)
+  BackDev bkd;
 };
 
 // shared-memory layout of layer_tc_kernel for input element size `el`; returns total bytes
@@ -576,6 +581,127 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
           TcOpDev tmp = t;
           op.tc_smem[v] = layout_tc(tmp, t.n_segs, v ? 1 : 4);
         }
+        // ---- single-layer FP16-split kernel (back_tc.cuh): float inputs bounded by the previous op's saturation, term
+        // segments of the kinds it has straight-line code for
+        op.back = false;
+        {
+          // opt-in (HGSFA_BACK=1): measured on U11L_64 it is correct and slightly more accurate than the 3xTF32 kernel but
+          // 15 % slower with 8 expansion warps per SM (14.5 vs 12.5 ms for ops 3-10, profiles/README_r02.md)
+          const char* env = getenv("HGSFA_BACK");
+          bool ok = env && env[0] == '1' && o > 0 && t.Npad16 <= 64 && t.n_chunks <= 64;
+          float bound_in = 0.f;
+          if (ok) {
+            const OpDev& prev = pl->ops[o - 1].dev;
+            bound_in = std::max(std::fabs(prev.clip_lo), std::fabs(prev.clip_hi));
+            ok = std::isfinite(bound_in) && bound_in > 0.f;
+          }
+          float pexp = 0.f;
+          int tri_row0 = 0, n_tri = 0;
+          for (const Seg& pc : tsegs) {
+            if (!ok) break;
+            if (pc.op == OP_ID || pc.op == OP_ABSPOW) {
+              ok = pc.ibase >= 0 && pc.ibase % 4 == 0;
+              if (pc.op == OP_ABSPOW) {
+                ok = ok && (pexp == 0.f || pexp == pc.p) && pc.p > 0.f && pc.p <= 1.f;
+                pexp = pc.p;
+              }
+            } else if (pc.op == OP_TRI) {
+              ok = int(pc.p) == BK_TRI_N && (n_tri == 0 || tri_row0 == pc.ibase);
+              tri_row0 = pc.ibase;
+              ++n_tri;
+            } else {
+              ok = false;
+            }
+          }
+          const int mean_floats = ((d.d_in + 7) & ~7) + 8;
+          ok = ok && t.Npad16 + mean_floats <= FR_HEAD / 4;
+          double max_mean = 0.0, max_w = 0.0;
+          int tri_shift = 0;
+          std::vector<uint8_t> is_tri(dp.K, 0);
+          if (ok) {
+            for (int w = 0; w < n_w; ++w)
+              for (int i = 0; i < d.d_in; ++i) max_mean = std::max(max_mean, (double)std::fabs(params[size_t(w) * d.param_floats + i]));
+            const double bound_c = double(bound_in) + max_mean;
+            ok = bound_c <= 16384.0;
+            while (bound_c / double(1 << tri_shift) > 128.0 && tri_shift < 12) ++tri_shift;     // products stay below 2^14
+            for (const Seg& pc : tsegs)
+              if (pc.op == OP_TRI)
+                for (int q = 0; q < pc.kind; ++q) is_tri[pc.pad1 + q] = 1;
+            const double tri_w = std::ldexp(1.0, 2 * tri_shift);
+            for (int w = 0; w < n_w && ok; ++w)
+              for (int k = 0; k < dp.K; ++k)
+                for (int n = 0; n < std::min(dp.Npad, t.Npad16); ++n)
+                  max_w = std::max(max_w, std::fabs((double)params[size_t(w) * d.param_floats + dp.w_off + size_t(k) * dp.Npad + n]) *
+                                              (is_tri[k] ? tri_w : 1.0));
+            ok = ok && max_w > 0.0 && std::isfinite(max_w);
+          }
+          if (ok) {
+            BackDev& b = op.bkd;
+            b = BackDev{};
+            b.n_nodes = d.n_nodes; b.d_in = d.d_in; b.in_dim = d.in_dim; b.out_dim = d.out_dim; b.shared = d.shared;
+            b.n_runs = d.n_runs; b.npc = 1; b.nn = t.Npad16; b.n_chunks = t.n_chunks; b.tri_row0 = tri_row0;
+            b.mean_floats = mean_floats; b.chunk_bytes = FR_HEAD + 32 * t.Npad16 * 4;
+            const int tpow = (int)std::floor(std::log2(16384.0 / max_w));
+            b.scale = (float)std::ldexp(1.0, -tpow);
+            b.clo = d.clip_lo; b.chi = d.clip_hi; b.p = pexp > 0.f ? pexp : 1.f;
+            b.tri_scale = (float)std::ldexp(1.0, -tri_shift);
+            ok = back_layout(b) > 0;
+            if (ok) {
+              // group table: four 8-term groups per chunk
+              std::vector<BkGroup> groups(size_t(t.n_chunks) * 4, BkGroup{BK_ID_RAW, 0, 1, 0});
+              for (const Seg& pc : tsegs) {
+                const int ngr = (pc.k1 - pc.k0) / 8;
+                for (int q = 0; q < ngr; ++q) {
+                  BkGroup& gq = groups[pc.k0 / 8 + q];
+                  const int cnt = std::max(1, std::min(8, pc.kind - 8 * q));
+                  if (pc.op == OP_TRI) gq = BkGroup{BK_TRI, 0, 8, pc.nomean / 8 + q};
+                  else gq = BkGroup{pc.op == OP_ABSPOW ? BK_POW : (pc.nomean ? BK_ID_RAW : BK_ID), pc.ibase + 8 * q, cnt, 0};
+                }
+              }
+              const size_t img_bytes = size_t(n_w) * t.n_chunks * b.chunk_bytes;
+              const size_t grp_bytes = groups.size() * sizeof(BkGroup);
+              const size_t oc_bytes = (size_t(d.n_nodes) * 4 + 15) & ~size_t(15);
+              std::vector<uint8_t> hb(img_bytes + grp_bytes + oc_bytes, 0);
+              const double wmul = std::ldexp(1.0, tpow), tri_w = std::ldexp(1.0, 2 * tri_shift);
+              const int nb8 = t.Npad16 / 8;
+              for (int w = 0; w < n_w; ++w) {
+                const float* pw = params + size_t(w) * d.param_floats;
+                uint8_t* node_img = hb.data() + size_t(w) * t.n_chunks * b.chunk_bytes;
+                float* head = reinterpret_cast<float*>(node_img);               // chunk 0: bias[nn] | mean[mean_floats]
+                for (int n = 0; n < std::min(dp.Npad, t.Npad16); ++n) head[n] = pw[dp.b_off + n];
+                for (int i = 0; i < d.d_in; ++i) head[t.Npad16 + i] = pw[i];
+                for (int k = 0; k < dp.K; ++k) {
+                  const int c = knew[k] / 32, kk = knew[k] % 32;
+                  __half* hi = reinterpret_cast<__half*>(node_img + size_t(c) * b.chunk_bytes + FR_HEAD);
+                  __half* lo = hi + 32 * t.Npad16;
+                  for (int n = 0; n < std::min(dp.Npad, t.Npad16); ++n) {
+                    const double wv = double(pw[dp.w_off + size_t(k) * dp.Npad + n]) * (is_tri[k] ? tri_w : 1.0) * wmul;
+                    const size_t off = (size_t((kk >> 3) * nb8 + (n >> 3)) * 8 + (n & 7)) * 8 + (kk & 7);
+                    const __half h = __float2half_rn(float(wv));
+                    hi[off] = h;
+                    lo[off] = __float2half_rn(float(wv - double(__half2float(h))));
+                  }
+                }
+              }
+              std::memcpy(hb.data() + img_bytes, groups.data(), grp_bytes);
+              int32_t* oc = reinterpret_cast<int32_t*>(hb.data() + img_bytes + grp_bytes);
+              for (int nd = 0; nd < d.n_nodes; ++nd) oc[nd] = out_col[nd] + col_off[nd];
+              pl->tc_bufs.emplace_back();
+              DevBuf& bb = pl->tc_bufs.back();
+              if (bb.reserve(hb.size())) return plan_fail(pl, "out of device memory for the FP16 operand images");
+              if (cudaMemcpy(bb.p, hb.data(), hb.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+                return plan_fail(pl, "FP16 operand upload failed");
+              const uint8_t* base_b = static_cast<const uint8_t*>(bb.p);
+              b.wimg = base_b;
+              b.groups = reinterpret_cast<const BkGroup*>(base_b + img_bytes);
+              b.out_col = reinterpret_cast<const int*>(base_b + img_bytes + grp_bytes);
+              b.n_valid = t.n_valid;
+              b.runs = d.runs;
+              if (back_set_attributes()) { std::string msg = last_error_ref(); return plan_fail(pl, "%s", msg.c_str()); }
+              op.back = true;
+            }
+          }
+        }
         if (op.tc_smem[0] > size_t(227) * 1024)
           return plan_fail(pl, "op %lld: tensor-core layout needs %zu bytes of shared memory", (long long)o, op.tc_smem[0]);
       }
@@ -825,8 +951,14 @@ int run_ops(hgsfa_plan_s* pl, int o0, int o1, const void* xin, bool xin_u8, floa
     hgsfa_plan_s::Stamp stamp{o, nullptr, nullptr};
     if (pl->profile && cudaEventCreate(&stamp.e0) == cudaSuccess && cudaEventCreate(&stamp.e1) == cudaSuccess)
       cudaEventRecord(stamp.e0, st);
-    int rc = op.tc ? (cur_u8 ? launch_layer_tc<uint8_t>(pl, op, cur, dst, ntiles, st) : launch_layer_tc<float>(pl, op, cur, dst, ntiles, st))
-                   : (cur_u8 ? launch_layer<uint8_t>(pl, op, cur, dst, ntiles, st) : launch_layer<float>(pl, op, cur, dst, ntiles, st));
+    int rc;
+    if (op.back && !cur_u8) {
+      rc = back_launch(op.bkd, pl->sm_count, static_cast<const float*>(cur), dst, ntiles, st);
+      pl->launches++;
+    } else {
+      rc = op.tc ? (cur_u8 ? launch_layer_tc<uint8_t>(pl, op, cur, dst, ntiles, st) : launch_layer_tc<float>(pl, op, cur, dst, ntiles, st))
+                 : (cur_u8 ? launch_layer<uint8_t>(pl, op, cur, dst, ntiles, st) : launch_layer<float>(pl, op, cur, dst, ntiles, st));
+    }
     if (rc) return rc;
     if (pl->profile && stamp.e1) {
       cudaEventRecord(stamp.e1, st);
@@ -863,7 +995,8 @@ extern "C" int hgsfa_plan_op_stats(hgsfa_plan_t pl, int64_t capacity, double* ms
   pl->stamps.clear();
   for (size_t o = 0; o < pl->ops.size(); ++o) {
     if (ms) ms[o] = pl->op_ms[o];
-    if (engine) engine[o] = (pl->front_ok && o < 3) ? 2 : (pl->ops[o].tc ? 1 : 0);   // 2: fused front (uint8 inputs), time booked on op 0
+    // 2: fused front (uint8 inputs; time booked on op 0), 3: single-layer FP16-split kernel (float inputs)
+    if (engine) engine[o] = (pl->front_ok && o < 3) ? 2 : (pl->ops[o].back ? 3 : (pl->ops[o].tc ? 1 : 0));
     if (alg_flops) alg_flops[o] = double(pl->ops[o].alg_flops);
     if (exe_flops) exe_flops[o] = double(pl->ops[o].exe_flops);
   }

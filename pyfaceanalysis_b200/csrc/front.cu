@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "front_tc.cuh"
+#include "back_tc.cuh"
 
 namespace hgsfa {
 
@@ -83,5 +84,40 @@ int front_launch(const FrontDev& fd_in, int np1, int np2, int img_h, int sm_coun
 
 
 bool front_tensor_maps_available() { return encode_tiled_fn() != nullptr; }
+
+// ---- single-layer FP16-split kernel ----
+size_t back_layout(BackDev& bd) {
+  bd.x_stage_bytes = int((size_t(bd.d_in) * TILE * 4 + 127) & ~size_t(127));
+  const size_t limit = size_t(227) * 1024;
+  for (int nstx = 2; nstx >= 1; --nstx) {
+    const size_t total = size_t(BK_SM_X) + size_t(2) * nstx * bd.x_stage_bytes;
+    if (total <= limit) {
+      bd.nstx = nstx;
+      return total;
+    }
+  }
+  return 0;
+}
+
+int back_set_attributes() {
+  HG_CUDA(cudaFuncSetAttribute(back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  return 0;
+}
+
+int back_launch(const BackDev& bd_in, int sm_count, const float* xin, float* xout, int64_t ntiles, cudaStream_t st) {
+  if (ntiles <= 0) return 0;
+  BackDev bd = bd_in;
+  const size_t smem = back_layout(bd);
+  HG_CHECK(smem > 0, "single-layer FP16 kernel: a receptive field of %d inputs does not fit in shared memory", bd.d_in);
+  // nodes per CTA: as many as possible (weights of node i+1 stream behind node i) while the grid still covers the SMs
+  const int64_t pairs = ceil_div(ntiles, 2);
+  int64_t npc = (pairs * bd.n_nodes) / (int64_t(sm_count) * 3);
+  npc = std::max<int64_t>(1, std::min<int64_t>(npc, std::min(bd.n_nodes, 32)));
+  bd.npc = int(npc);
+  dim3 grid((unsigned)pairs, (unsigned)ceil_div(bd.n_nodes, bd.npc));
+  back_kernel<<<grid, BK_THREADS, smem, st>>>(bd, xin, xout, ntiles, BK_SM_X);
+  HG_CUDA(cudaGetLastError());
+  return 0;
+}
 
 }  // namespace hgsfa

@@ -17,10 +17,15 @@
 // relative error of a contraction is 4e-7 (3xTF32: 5e-7).  Operands are range-checked on the host
 // (pyfaceanalysis_b200/front.py: pixels, clipped activations, weights rescaled by 2^t per level).
 //
-// CTA = 11 warps, one per SM (all 512 tensor-memory columns):
-//   warps 0-3 / 4-7  expansion of tile group 0 / 1 (two tiles of 128 windows share every weight chunk)
-//   warps 8 / 9      MMA issue for group 0 / 1 (one elected lane)
-//   warp 10          producer: pixel boxes (3-D tensor map over row-major windows, or bulk copies of window-minor
+// CTA = 19 warps, one per SM (all 512 tensor-memory columns):
+//   warps 0-7 / 8-15 expansion of tile group 0 / 1 (two tiles of 128 windows share every weight chunk).  A group's 128
+//                    tensor-memory lanes are served by TWO warps per lane quarter, which split every item between them
+//                    (a node's pixels 0-7 / 8-15, child 0 / child 1 of a join, output columns 0-15 / 16-31): with 8
+//                    expansion warps the kernel was bound by the dependent-issue latency of 2 warps per scheduler
+//                    (profiles/ncu_r02_front_*.txt: issue slots 48 % used, top stall "wait"), tensor memory has no room
+//                    for a third tile group, so the parallelism comes from inside the tile
+//   warps 16 / 17    MMA issue for group 0 / 1 (one elected lane)
+//   warp 18          producer: pixel boxes (3-D tensor map over row-major windows, or bulk copies of window-minor
 //                    tiles) and weight chunks (cp.async.bulk) through mbarrier rings
 // Item order per subtree s (software-pipelined so that no item depends on the one issued just before it):
 //   L0a(s) L0b(s) L2(s-1) L0c(s) L0d(s) L1ab(s) STORE(s-1) L1cd(s)
@@ -39,7 +44,8 @@ constexpr int FR_NA = 3;                 // A-ring stages per group (32 columns 
 constexpr int FR_NX = 2;                 // pixel-box stages per group
 constexpr int FR_WSTAGE = FR_HEAD + 32 * 128;
 constexpr int FR_XSTAGE = 16 * 8 * TILE;  // 16 x 8 pixel box of 128 windows
-constexpr int FR_THREADS = 11 * 32;
+constexpr int FR_EXP_WARPS = 16;         // two tile groups x two warps per lane quarter
+constexpr int FR_THREADS = (FR_EXP_WARPS + 3) * 32;
 #ifndef HGSFA_FR_SLEEP_MMA
 #define HGSFA_FR_SLEEP_MMA 64
 #endif
@@ -57,8 +63,8 @@ constexpr int FR_COL_L0 = 0, FR_COL_L1 = 64, FR_COL_L2 = 128, FR_COL_A = 160;
 enum { FRB_WFULL = 0, FRB_WFREE = FR_NW, FRB_G = 2 * FR_NW, FRB_AFULL = 0, FRB_AFREE = FR_NA, FRB_DFULL = 2 * FR_NA,
        FRB_XFULL = 2 * FR_NA + 7, FRB_XFREE = 2 * FR_NA + 7 + FR_NX, FRB_GSTRIDE = 2 * FR_NA + 7 + 2 * FR_NX,
        FRB_COUNT = 2 * FR_NW + 2 * FRB_GSTRIDE };
-constexpr int FR_SM_BARS = 0, FR_SM_TMEM = 512, FR_SM_BIAS = 1024;               // bias: 8 warps x 32 floats
-constexpr int FR_SM_W = 2048, FR_SM_X = FR_SM_W + FR_NW * FR_WSTAGE + 512;        // pixel stages are 1024-aligned (below)
+constexpr int FR_SM_BARS = 0, FR_SM_TMEM = 512, FR_SM_BIAS = 1024;               // bias: 16 warps x 32 floats
+constexpr int FR_SM_W = 1024 + 2048, FR_SM_X = FR_SM_W + FR_NW * FR_WSTAGE + 512;        // pixel stages are 1024-aligned (below)
 constexpr int FR_SMEM = ((FR_SM_X + 1023) & ~1023) + 2 * FR_NX * FR_XSTAGE + 1024;
 
 __device__ __forceinline__ bool fr_try(uint32_t addr, uint32_t parity) {
@@ -67,13 +73,27 @@ __device__ __forceinline__ bool fr_try(uint32_t addr, uint32_t parity) {
                : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
   return ok != 0;
 }
+// barrier operations on 32-bit shared-window addresses (computed once per role: no generic-to-shared conversion per call)
+__device__ __forceinline__ void fr_arrive(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void fr_expect_tx(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fr_commit(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void fr_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 template <int SLEEP_NS = 0>
-__device__ __forceinline__ void fr_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void fr_wait(uint32_t addr, uint32_t parity) {
   // try_wait is meant to suspend the warp in hardware (alone it does, ~4 us per call: profiles/tc_probe2_r02.txt) but inside
   // this kernel it returns within tens of ns (profiles/ncu_r02_front_lines.txt: 17 % of the executed instructions were
   // re-tries), so the service warps (MMA issue, producer) sleep between tries instead of stealing issue slots from the
   // expansion warps of their scheduler.  A protocol error traps instead of hanging the GPU.
-  const uint32_t addr = smem_u32(bar);
 #pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     if (fr_try(addr, parity)) return;
@@ -87,6 +107,8 @@ __device__ __forceinline__ void fr_wait(uint64_t* bar, uint32_t parity) {
   }
   __trap();
 }
+template <int SLEEP_NS = 0>
+__device__ __forceinline__ void fr_wait(uint64_t* bar, uint32_t parity) { fr_wait<SLEEP_NS>(smem_u32(bar), parity); }
 __device__ __forceinline__ uint32_t fr_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
 __device__ __forceinline__ void fr_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -101,6 +123,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
       "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -132,53 +158,53 @@ __device__ __forceinline__ void fr_tensor_load(void* dst, const CUtensorMap* tma
       : "memory");
 }
 
-// ---- expansion of a join node (levels 1 and 2): the children's accumulators -> A chunks of 32 terms ----
+// ---- expansion of a join node (levels 1 and 2): a child's accumulator -> this warp's half of every A chunk ----
+// Two warps share a lane quarter: warp `half` expands child `half` of the node.  Its 2 NP terms (identity of the child's
+// NP columns, then |x - m|^p of the same columns) fill 16 of the 32 terms of each of the NP / 8 chunks, so neither warp
+// ever touches the other child's accumulator (pyfaceanalysis_b200/front.py orders the weight rows accordingly).
 template <int NP>
 struct FrJoin {
-  // values of the 2 NP inputs after the children's bias and saturation
   template <typename PUB>
-  static __device__ __forceinline__ void run(uint32_t acc0, uint32_t acc1, const float* head, float s, float clo, float chi,
-                                             float p, PUB&& publish) {
-    float y[2 * NP];
+  static __device__ __forceinline__ void run(uint32_t acc, const float* bias, const float* mean, int half, float s, float clo,
+                                             float chi, float p, PUB&& publish) {
+    float y[NP];
     {
-      uint32_t r[2 * NP];
-      tmem_ld_cols<NP>(acc0, r);
-      tmem_ld_cols<NP>(acc1, r + NP);
+      uint32_t r[NP];
+      tmem_ld_cols<NP>(acc, r);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int k = 0; k < 2 * NP; k += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(head + k);
+      for (int k = 0; k < NP; k += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + k);
         y[k + 0] = fminf(fmaxf(fmaf(__uint_as_float(r[k + 0]), s, b.x), clo), chi);
         y[k + 1] = fminf(fmaxf(fmaf(__uint_as_float(r[k + 1]), s, b.y), clo), chi);
         y[k + 2] = fminf(fmaxf(fmaf(__uint_as_float(r[k + 2]), s, b.z), clo), chi);
         y[k + 3] = fminf(fmaxf(fmaf(__uint_as_float(r[k + 3]), s, b.w), clo), chi);
       }
     }
-    const float* mean = head + 2 * NP;
-    constexpr int NCH = 4 * NP / 32;
+    constexpr int NCH = NP / 8;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      uint32_t hi[16], lo[16];
+      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int q = 0; q < 16; q += 2) {          // four terms per step: one LDS.128 of means serves the power terms
-        const int t = 32 * c + 2 * q;            // multiple of 4
+      for (int q = 0; q < 8; q += 2) {           // four terms per step: one LDS.128 of means serves the power terms
+        const int t = 16 * c + 2 * q;            // position in this warp's term sequence, multiple of 4
         float v[4];
-        if (t < 2 * NP) {
+        if (t < NP) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[e] = y[t + e];
         } else {
-          const float4 m = *reinterpret_cast<const float4*>(mean + (t - 2 * NP));
-          v[0] = abspow(y[t - 2 * NP + 0] - m.x, p);
-          v[1] = abspow(y[t - 2 * NP + 1] - m.y, p);
-          v[2] = abspow(y[t - 2 * NP + 2] - m.z, p);
-          v[3] = abspow(y[t - 2 * NP + 3] - m.w, p);
+          const float4 m = *reinterpret_cast<const float4*>(mean + (t - NP));
+          v[0] = abspow(y[t - NP + 0] - m.x, p);
+          v[1] = abspow(y[t - NP + 1] - m.y, p);
+          v[2] = abspow(y[t - NP + 2] - m.z, p);
+          v[3] = abspow(y[t - NP + 3] - m.w, p);
         }
         fr_split(v[0], v[1], hi[q], lo[q]);
         fr_split(v[2], v[3], hi[q + 1], lo[q + 1]);
       }
-      const uint32_t col = publish.acquire();      // also hands the previous chunk to the MMA warp: its stores had this
-      tmem_st16(col, hi);                          // chunk's arithmetic to complete behind
-      tmem_st16(col + 16, lo);
+      const uint32_t col = publish.acquire() + uint32_t(8 * half);
+      tmem_st8(col, hi);
+      tmem_st8(col + 16, lo);
       publish.release();
     }
   }
@@ -198,7 +224,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
   const int s_end = min(fd.n_sub, s_begin + fd.sub_per_cta);
   // the two tile groups of the CTA; an odd tile count lets the last CTA compute its only tile twice (identical stores)
   const int64_t tile_g0 = min(int64_t(blockIdx.x) * 2, ntiles - 1), tile_g1 = min(int64_t(blockIdx.x) * 2 + 1, ntiles - 1);
-  constexpr int NCH1 = 4 * NP1 / 32, NCH2 = 4 * NP2 / 32;
+  constexpr int NCH1 = NP1 / 8, NCH2 = NP2 / 8;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
@@ -208,9 +234,9 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
     for (int i = 0; i < FR_NW; ++i) { mbar_init(&bars[FRB_WFULL + i], 1); mbar_init(&bars[FRB_WFREE + i], 2); }
     for (int g = 0; g < 2; ++g) {
       uint64_t* gb = bars + FRB_G + g * FRB_GSTRIDE;
-      for (int i = 0; i < FR_NA; ++i) { mbar_init(&gb[FRB_AFULL + i], 4); mbar_init(&gb[FRB_AFREE + i], 1); }
+      for (int i = 0; i < FR_NA; ++i) { mbar_init(&gb[FRB_AFULL + i], 8); mbar_init(&gb[FRB_AFREE + i], 1); }
       for (int i = 0; i < 7; ++i) mbar_init(&gb[FRB_DFULL + i], 1);
-      for (int i = 0; i < FR_NX; ++i) { mbar_init(&gb[FRB_XFULL + i], 1); mbar_init(&gb[FRB_XFREE + i], 4); }
+      for (int i = 0; i < FR_NX; ++i) { mbar_init(&gb[FRB_XFULL + i], 1); mbar_init(&gb[FRB_XFREE + i], 8); }
     }
     mbar_fence_init();
   }
@@ -219,7 +245,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
 
-  if (warp == 10) {
+  if (warp == FR_EXP_WARPS + 2) {
     // ================================ producer ================================
     if (lane == 0) {
       Ring rw(FR_NW), rx(FR_NX);
@@ -272,10 +298,10 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
       }
     }
     __syncwarp();
-  } else if (warp >= 8) {
+  } else if (warp >= FR_EXP_WARPS) {
     // ================================ MMA issue (one warp per tile group) ================================
-    const int g = warp - 8;
-    uint64_t* gb = bars + FRB_G + g * FRB_GSTRIDE;
+    const int g = warp - FR_EXP_WARPS;
+    const uint32_t gbu = smem_u32(bars + FRB_G + g * FRB_GSTRIDE), barsu = smem_u32(bars);
     const bool leader = elect_one();
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0) + uint32_t(g * FR_GCOLS);
     Ring rw(FR_NW), ra(FR_NA);
@@ -285,8 +311,8 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
       const int ws0 = rw.idx;
 #pragma unroll 1
       for (int c = 0; c < nch; ++c, rw.next(), ra.next()) {
-        fr_wait<FR_SLEEP_MMA>(&bars[FRB_WFULL + rw.idx], rw.par);
-        fr_wait<FR_SLEEP_MMA>(&gb[FRB_AFULL + ra.idx], ra.par);
+        fr_wait<FR_SLEEP_MMA>(barsu + 8u * uint32_t(FRB_WFULL + rw.idx), rw.par);
+        fr_wait<FR_SLEEP_MMA>(gbu + 8u * uint32_t(FRB_AFULL + ra.idx), ra.par);
         tc_fence_after();
         if (leader) {
           const uint32_t wbase = smem_u32(wring + size_t(rw.idx) * FR_WSTAGE + FR_HEAD);
@@ -299,12 +325,12 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
             fr_mma(tb + dcol, a_hi + 8u * j, blo, idesc, 1u);
             if (!(first_exact && j == 0)) fr_mma(tb + dcol, a_lo + 8u * j, bhi, idesc, 1u);   // pixels are exact in FP16
           }
-          tc_commit(&gb[FRB_AFREE + ra.idx]);
+          fr_commit(gbu + 8u * uint32_t(FRB_AFREE + ra.idx));
           // the first chunk of an item carries the head the expansion warps read for every chunk: it is released last
-          if (c > 0 || nch == 1) tc_commit(&bars[FRB_WFREE + rw.idx]);
+          if (c > 0 || nch == 1) fr_commit(barsu + 8u * uint32_t(FRB_WFREE + rw.idx));
           if (c == nch - 1) {
-            if (nch > 1) tc_commit(&bars[FRB_WFREE + ws0]);
-            tc_commit(&gb[FRB_DFULL + dslot]);
+            if (nch > 1) fr_commit(barsu + 8u * uint32_t(FRB_WFREE + ws0));
+            fr_commit(gbu + 8u * uint32_t(FRB_DFULL + dslot));
           }
         }
         __syncwarp();
@@ -327,9 +353,11 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
     }
   } else {
     // ================================ expansion (thread = window) ================================
-    const int g = warp >> 2;
-    const int win = tid & (TILE - 1);
-    uint64_t* gb = bars + FRB_G + g * FRB_GSTRIDE;
+    // warps 0-7 tile group 0, 8-15 group 1; inside a group warps 0-3 are "half 0" of the four lane quarters, 4-7 "half 1":
+    // the two halves of a quarter split every item between them (pixels 0-7 / 8-15, child 0 / child 1, columns 0-15 / 16-31)
+    const int g = warp >> 3, half = (warp >> 2) & 1;
+    const int win = (warp & 3) * 32 + lane;
+    const uint32_t gbu = smem_u32(bars + FRB_G + g * FRB_GSTRIDE), barsu = smem_u32(bars);
     const uint32_t lane_base = tbase + (uint32_t((warp & 3) * 32) << 16) + uint32_t(g * FR_GCOLS);
     float* bias_out = reinterpret_cast<float*>(smem + FR_SM_BIAS) + warp * 32;
     const int64_t tile = g ? tile_g1 : tile_g0;
@@ -339,7 +367,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
     // notes that its stores were issued; the next acquire() or flush() waits for them and arrives), so that the stores
     // complete behind the next chunk's arithmetic -- measured 3 % SLOWER (profiles/README_r02.md), hence off.
     struct Publisher {
-      uint64_t* gb;
+      uint32_t gbu;
       Ring& ra;
       uint32_t lane_base;
       int lane;
@@ -349,13 +377,13 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&gb[FRB_AFULL + pending]);
+          if (lane == 0) fr_arrive(gbu + 8u * uint32_t(FRB_AFULL + pending));
           pending = -1;
         }
       }
       __device__ __forceinline__ uint32_t acquire() {
         flush();
-        fr_wait(&gb[FRB_AFREE + ra.idx], ra.par ^ 1u);
+        fr_wait(gbu + 8u * uint32_t(FRB_AFREE + ra.idx), ra.par ^ 1u);
         tc_fence_after();
         return lane_base + uint32_t(FR_COL_A + 32 * ra.idx);
       }
@@ -364,94 +392,97 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
         ra.next();
         if (!FR_LAZY_PUBLISH) flush();
       }
-    } pub{gb, ra, lane_base, lane, -1};
+    } pub{gbu, ra, lane_base, lane, -1};
 
     auto head_of = [&](int stage) { return reinterpret_cast<const float*>(wring + size_t(stage) * FR_WSTAGE); };
 
     auto item_l0 = [&](int sub, int i) {
       const int q = sub & 1;
-      if (i == 0 && q == 0) fr_wait(&gb[FRB_XFULL + rx.idx], rx.par);
+      if (i == 0 && q == 0) fr_wait(gbu + 8u * uint32_t(FRB_XFULL + rx.idx), rx.par);
       const uint8_t* box = xring + size_t(g * FR_NX + rx.idx) * FR_XSTAGE;
       const int off = __ldg(fd.l0_off + sub * 4 + i);
       const int dy = off & 0xff, dx = off >> 8;
-      float px[16];
+      float px[8];                                             // rows 2 half, 2 half + 1 of the node's 4 x 4 pixels
       if (IN_MODE == FR_IN_ROWMAJOR) {
         // box = [8 rows][128 windows][16 bytes] (tensor dimensions ordered x, window, y): consecutive lanes read words
         // 16 bytes apart -- 4 wavefronts per load, as many as the byte loads of the window-minor form need
         const uint8_t* wrow = box + win * 16 + dx;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const uint32_t u = *reinterpret_cast<const uint32_t*>(wrow + (dy + r) * (16 * TILE));
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(wrow + (dy + 2 * half + r) * (16 * TILE));
           const float4 f = u8x4_to_float4(u);
           px[4 * r + 0] = f.x; px[4 * r + 1] = f.y; px[4 * r + 2] = f.z; px[4 * r + 3] = f.w;
         }
       } else {
         // box = [8 rows][16 pixels][128 windows]
-        const uint8_t* col = box + (dy * 16 + dx) * TILE + win;
+        const uint8_t* col = box + ((dy + 2 * half) * 16 + dx) * TILE + win;
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
           for (int x = 0; x < 4; ++x)
             px[4 * r + x] = __uint_as_float(0x4B000000u | uint32_t(col[(r * 16 + x) * TILE])) - 8388608.0f;
       }
-      fr_wait(&bars[FRB_WFULL + rw.idx], rw.par);
-      const float* mean = head_of(rw.idx);
+      fr_wait(barsu + 8u * uint32_t(FRB_WFULL + rw.idx), rw.par);
+      const float* mean = head_of(rw.idx) + 8 * half;
       rw.next();
-      uint32_t hi[16], lo[8];
+      uint32_t hi_id[4], hi_pw[4], lo_pw[4];
 #pragma unroll
-      for (int k = 0; k < 16; k += 4) {
+      for (int k = 0; k < 8; k += 4) {
         const float4 m = *reinterpret_cast<const float4*>(mean + k);
-        hi[k / 2] = fr_pack(px[k], px[k + 1]);                 // identity terms: 8-bit integers, exact in FP16
-        hi[k / 2 + 1] = fr_pack(px[k + 2], px[k + 3]);
-        fr_split(abspow(px[k] - m.x, fd.p0), abspow(px[k + 1] - m.y, fd.p0), hi[8 + k / 2], lo[k / 2]);
-        fr_split(abspow(px[k + 2] - m.z, fd.p0), abspow(px[k + 3] - m.w, fd.p0), hi[8 + k / 2 + 1], lo[k / 2 + 1]);
+        hi_id[k / 2] = fr_pack(px[k], px[k + 1]);              // identity terms: 8-bit integers, exact in FP16
+        hi_id[k / 2 + 1] = fr_pack(px[k + 2], px[k + 3]);
+        fr_split(abspow(px[k] - m.x, fd.p0), abspow(px[k + 1] - m.y, fd.p0), hi_pw[k / 2], lo_pw[k / 2]);
+        fr_split(abspow(px[k + 2] - m.z, fd.p0), abspow(px[k + 3] - m.w, fd.p0), hi_pw[k / 2 + 1], lo_pw[k / 2 + 1]);
       }
-      const uint32_t col = pub.acquire();
-      tmem_st16(col, hi);
-      tmem_st8(col + 24, lo);                                  // lo pieces of the power terms (K step 1)
+      // A stage of the node: hi columns 0-7 identity (K step 0), 8-15 power (K step 1); lo columns 16 + the same
+      const uint32_t col = pub.acquire() + uint32_t(4 * half);
+      tmem_st4(col, hi_id);
+      tmem_st4(col + 8, hi_pw);
+      tmem_st4(col + 24, lo_pw);
       pub.release();
       if (i == 3 && q == 1) {                                  // pixel box of the pair consumed
         __syncwarp();
-        if (lane == 0) mbar_arrive(&gb[FRB_XFREE + rx.idx]);
+        if (lane == 0) fr_arrive(gbu + 8u * uint32_t(FRB_XFREE + rx.idx));
         rx.next();
       }
     };
     auto item_l1 = [&](int h, uint32_t par) {
       pub.flush();
-      fr_wait(&gb[FRB_DFULL + 2 * h], par);
-      fr_wait(&gb[FRB_DFULL + 2 * h + 1], par);
+      fr_wait(gbu + 8u * uint32_t(FRB_DFULL + 2 * h + half), par);            // this warp expands child `half` of the join
       tc_fence_after();
-      fr_wait(&bars[FRB_WFULL + rw.idx], rw.par);
+      fr_wait(barsu + 8u * uint32_t(FRB_WFULL + rw.idx), rw.par);
       const float* head = head_of(rw.idx);
       rw.advance(NCH1);
-      FrJoin<NP1>::run(lane_base + FR_COL_L0 + 32 * h, lane_base + FR_COL_L0 + 32 * h + 16, head, fd.s0, fd.clo0, fd.chi0, fd.p1, pub);
+      FrJoin<NP1>::run(lane_base + FR_COL_L0 + 32 * h + 16 * half, head + NP1 * half, head + 2 * NP1 + NP1 * half, half, fd.s0,
+                       fd.clo0, fd.chi0, fd.p1, pub);
     };
     auto item_l2 = [&](uint32_t par) {
       pub.flush();
-      fr_wait(&gb[FRB_DFULL + 4], par);
-      fr_wait(&gb[FRB_DFULL + 5], par);
+      fr_wait(gbu + 8u * uint32_t(FRB_DFULL + 4 + half), par);
       tc_fence_after();
-      fr_wait(&bars[FRB_WFULL + rw.idx], rw.par);
+      fr_wait(barsu + 8u * uint32_t(FRB_WFULL + rw.idx), rw.par);
       const float* head = head_of(rw.idx);
       rw.advance(NCH2);
       __syncwarp();
       bias_out[lane] = head[4 * NP2 + lane];                   // kept for the store item (the weight stage is recycled)
       __syncwarp();
-      FrJoin<NP2>::run(lane_base + FR_COL_L1, lane_base + FR_COL_L1 + 32, head, fd.s1, fd.clo1, fd.chi1, fd.p2, pub);
+      FrJoin<NP2>::run(lane_base + FR_COL_L1 + 32 * half, head + NP2 * half, head + 2 * NP2 + NP2 * half, half, fd.s1, fd.clo1,
+                       fd.chi1, fd.p2, pub);
     };
     auto item_store = [&](int sub, uint32_t par) {
       pub.flush();
-      fr_wait(&gb[FRB_DFULL + 6], par);
+      fr_wait(gbu + 8u * uint32_t(FRB_DFULL + 6), par);
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_cols<32>(lane_base + FR_COL_L2, r);
+      uint32_t r[16];                                          // this warp's half of the node's 32 columns
+      tmem_ld_cols<16>(lane_base + FR_COL_L2 + 16 * half, r);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float* out = xout + (size_t(tile) * fd.out_dim + __ldg(fd.out_col + sub)) * TILE + win;
-      const int nv = fd.nv_out;
+      float* out = xout + (size_t(tile) * fd.out_dim + __ldg(fd.out_col + sub) + 16 * half) * TILE + win;
+      const int nv = fd.nv_out - 16 * half;
+      const float* bias = bias_out + 16 * half;
 #pragma unroll
-      for (int k = 0; k < 32; k += 4) {
+      for (int k = 0; k < 16; k += 4) {
         if (k < nv) {                                          // warp-uniform: one branch per four columns
-          const float4 b = *reinterpret_cast<const float4*>(bias_out + k);
+          const float4 b = *reinterpret_cast<const float4*>(bias + k);
           const float y0 = fminf(fmaxf(fmaf(__uint_as_float(r[k + 0]), fd.s2, b.x), fd.clo2), fd.chi2);
           const float y1 = fminf(fmaxf(fmaf(__uint_as_float(r[k + 1]), fd.s2, b.y), fd.clo2), fd.chi2);
           const float y2 = fminf(fmaxf(fmaf(__uint_as_float(r[k + 2]), fd.s2, b.z), fd.clo2), fd.chi2);

@@ -18,8 +18,10 @@ This module recognises the pattern in a compiled :class:`plan.PlanSpec` and buil
   ``[k/8][n/8][n%8][k%8]`` of 16-bit elements.
 * tables: pixel origin of every subtree pair, pixel offsets of the four first-layer nodes, output column.
 
-Term order of a join level (two children, ``NP`` = child width padded to 8):
-``t = c*NP + j`` identity of column j of child c; ``t = 2*NP + c*NP + j`` its |x - mean|^p.
+Term order of a join level (two children, ``NP`` = child width padded to 8): the kernel gives each child to one warp,
+whose term sequence ``s = 0 .. 2 NP - 1`` is ``s < NP``: identity of column s, else |x - mean|^p of column ``s - NP``; the
+two warps fill the two 16-term halves of every 32-term chunk, so term ``s`` of child ``c`` sits in A column
+``t = 32 (s // 16) + 16 c + s % 16``.
 """
 from __future__ import annotations
 
@@ -123,6 +125,11 @@ def _pad(v, n):
     out = np.zeros(n)
     out[:len(v)] = v
     return out
+
+
+def join_column(NP, child, s):
+    """A column of term ``s`` (position in the child's sequence [identity NP | power NP]) of child ``child``."""
+    return 32 * (s // 16) + 16 * child + s % 16
 
 
 class FrontSpec(object):
@@ -243,8 +250,8 @@ def build(spec):
         for c in range(2):
             for j in range(nv_child):
                 i = c * nv_child + j
-                rows[c * NP + j] = W_id[w, i]
-                rows[2 * NP + c * NP + j] = W_pow[w, i]
+                rows[join_column(NP, c, j)] = W_id[w, i]
+                rows[join_column(NP, c, NP + j)] = W_pow[w, i]
                 mean[c * NP + j] = m[w, i]
         return rows * 2.0 ** tpow[level], mean
 

@@ -155,7 +155,8 @@ class GpuFlow(object):
         ms, alg, exe = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
         eng = (C.c_int32 * n)()
         _lib.check(_lib.load().hgsfa_plan_op_stats(self._handle, n, ms, C.cast(eng, C.c_void_p), alg, exe))
-        names = {0: "ffma", 1: "tc", 2: "front"}     # "front": layers 0-2 fused in one kernel, time booked on op 0
+        # "front": layers 0-2 fused in one kernel (time booked on op 0); "f16": single-layer FP16-split tcgen05 kernel
+        names = {0: "ffma", 1: "tc", 2: "front", 3: "f16"}
         return [dict(ms=ms[i], engine=names.get(eng[i], "?"), alg_flops=alg[i], exe_flops=exe[i]) for i in range(n)]
 
     def set_chunks(self, front=0, back=0):

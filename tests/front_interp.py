@@ -46,8 +46,12 @@ def run_front(f, x):
             parts = [take(level) for _ in range(f.nch[level])]
             head = parts[0][0]
             W = np.concatenate([p[1] for p in parts], axis=0)
-            y = np.concatenate([np.clip(kids[c][:, :NP] * s_child + head[c * NP:(c + 1) * NP], *clip_child) for c in range(2)], axis=1)
-            A = np.concatenate([y, np.abs(y - head[2 * NP:4 * NP]) ** f.pexp[level]], axis=1)
+            A = np.zeros((n, 4 * NP))
+            for c in range(2):          # one warp per child: its [identity | power] sequence fills its half of every chunk
+                y = np.clip(kids[c][:, :NP] * s_child + head[c * NP:(c + 1) * NP], *clip_child)
+                seq = np.concatenate([y, np.abs(y - head[2 * NP + c * NP:2 * NP + (c + 1) * NP]) ** f.pexp[level]], axis=1)
+                for s_ in range(2 * NP):
+                    A[:, fr.join_column(NP, c, s_)] = seq[:, s_]
             return A @ W, head
         acc1 = [join(1, f.np1, acc0[2 * h:2 * h + 2], f.scale[0], f.clip[0])[0] for h in range(2)]
         acc2, head2 = join(2, f.np2, acc1, f.scale[1], f.clip[1])

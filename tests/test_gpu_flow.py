@@ -286,3 +286,21 @@ def test_plan_creation_order_does_not_matter(u11l96_flow, tiny_flow):
     assert np.isfinite(y).all() and small.execute(synthetic.synthetic_patches(5, (16, 16), 1)).shape == (5, 16)
     big.close()
     small.close()
+
+
+def test_single_layer_fp16_kernel_opt_in(u11l_flow, monkeypatch):
+    """HGSFA_BACK=1: the layers behind the fused front run on the single-layer FP16-split kernel (csrc/back_tc.cuh) --
+    kept because it is the more accurate of the two tensor-core layer kernels, off by default because it is slower."""
+    from pyfaceanalysis_b200 import GpuFlow, synthetic
+    monkeypatch.setenv("HGSFA_BACK", "1")
+    g = GpuFlow(u11l_flow)
+    monkeypatch.delenv("HGSFA_BACK")
+    x = synthetic.synthetic_patches(300, (64, 64), 31)
+    e = _check(g, u11l_flow, x, std=u11l_flow._train_output_std)
+    g.profile(True)
+    g.execute(x)
+    assert [s["engine"] for s in g.op_stats()] == ["front"] * 3 + ["f16"] * 8
+    print("U11L_64 front + f16 layers max err/std", e)
+    xf = x[:130].astype(np.float32)                 # float input: every layer but the first (no input bound) on the FP16 kernel
+    _check(g, u11l_flow, xf, std=u11l_flow._train_output_std)
+    g.close()
