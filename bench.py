@@ -320,7 +320,7 @@ def run_detect(args, rank, world, local_rank, dev, barrier, dist):
                        "d2h_bytes_per_step": int(sum(len(o) for o in allr) * 80 // max(world, 1)),
                        "api": "FaceDetector.prescale + FaceDetector.detect on pinned host images"},
                "stage_ms": {k: round(v[0] * 1e3, 3) for k, v in stage_bench.tasks.items()},
-               "crop_roofline": {"bound": "hbm", "kernel": "hgsfa::crop_index_kernel + crop_gather_kernel (row-major patches)",
+               "crop_roofline": {"bound": "hbm", "kernel": "hgsfa::crop_rows_u8_kernel (row-major uint8 patches)",
                                  "windows_cropped": int(sum(crops)), "achieved": crop_bytes / crop_s / 1e9 if crop_s > 0 else None,
                                  "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": crop_bytes / crop_s / 1e9 / peaks["hbm_gbs"] if crop_s > 0 else None,

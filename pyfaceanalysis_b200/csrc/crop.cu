@@ -392,9 +392,9 @@ __global__ void __launch_bounds__(256) crop_tiled_kernel(const uint8_t* img0, in
 // CTA = CROP_RW windows, 256 threads.
 //   1. thread (window, axis) builds the NEAREST index table of its window in shared memory (Pillow's sequential double
 //      accumulation, as in crop_index_kernel) and resolves the window's image pointer / size / angle.
-//   2. a warp takes one window at a time; a lane produces 16 consecutive pixels of a row -- 16 independent byte
-//      gathers in flight (the image is L2 / L1 resident), packed with PRMT into ONE 16-byte store; a warp's stores cover
-//      512 contiguous bytes (8 patch rows).  Rotated / BILINEAR / BICUBIC windows take the generic per-pixel path.
+//   2. a warp takes one window at a time; a lane produces 4 consecutive pixels of a row (4 byte gathers from the L1 / L2
+//      resident image, packed into one 4-byte store; a warp's stores cover 128 contiguous bytes = 2 patch rows).
+//      Rotated / BILINEAR / BICUBIC windows take the generic per-pixel path.
 constexpr int CROP_RW = 32;
 __global__ void __launch_bounds__(256) crop_rows_u8_kernel(const uint8_t* img0, int H0, int W0, const double* __restrict__ boxes,
                                                            const double* __restrict__ angles, int64_t n, int ow, int oh,
@@ -440,40 +440,34 @@ __global__ void __launch_bounds__(256) crop_rows_u8_kernel(const uint8_t* img0, 
     }
   }
   __syncthreads();
-  const int chunks_per_row = ow / 16, n_chunks = chunks_per_row * oh;
+  // a lane produces 4 consecutive pixels: the 16 lanes of a patch row read neighbouring source bytes (few cache lines
+  // per gather instruction -- with 16 pixels per lane a warp's gathers were spread over 8 image rows and the L1
+  // wavefronts, not HBM, set the pace: 2.85 ms for 503 k windows), and a warp's 4-byte stores cover 128 contiguous bytes
+  const int chunks_per_row = ow / 4, n_chunks = chunks_per_row * oh;
   for (int wl = warp; wl < CROP_RW; wl += 8) {
     const int64_t w = w0 + wl;
     if (w >= n) break;
     const uint8_t* img = w_img[wl];
     const int W = w_W[wl], H = w_H[wl];
     const double ang = w_ang[wl];
-    uint4* out = reinterpret_cast<uint4*>(dst + size_t(w) * ow * oh);
+    uint32_t* out = reinterpret_cast<uint32_t*>(dst + size_t(w) * ow * oh);
     if (ang == 0.0 && filter == HGSFA_NEAREST) {
       const int* xt = xs + wl * ow;
       const int* yt = ys + wl * oh;
+#pragma unroll 4
       for (int ch = lane; ch < n_chunks; ch += 32) {
-        const int r = ch / chunks_per_row, c0 = (ch - r * chunks_per_row) * 16;
+        const int r = ch / chunks_per_row, c0 = (ch - r * chunks_per_row) * 4;
         const int y = yt[r];
-        uint32_t px[16];
+        uint32_t v = 0u;
         if (y >= 0) {
           const uint8_t* row = img + size_t(y) * W;
-#pragma unroll
-          for (int k = 0; k < 16; k += 4) {
-            const int4 x = *reinterpret_cast<const int4*>(xt + c0 + k);
-            px[k + 0] = x.x >= 0 ? uint32_t(__ldg(row + x.x)) : 0u;
-            px[k + 1] = x.y >= 0 ? uint32_t(__ldg(row + x.y)) : 0u;
-            px[k + 2] = x.z >= 0 ? uint32_t(__ldg(row + x.z)) : 0u;
-            px[k + 3] = x.w >= 0 ? uint32_t(__ldg(row + x.w)) : 0u;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) px[k] = 0u;
+          const int4 x = *reinterpret_cast<const int4*>(xt + c0);
+          const uint32_t p0 = x.x >= 0 ? uint32_t(__ldg(row + x.x)) : 0u;
+          const uint32_t p1 = x.y >= 0 ? uint32_t(__ldg(row + x.y)) : 0u;
+          const uint32_t p2 = x.z >= 0 ? uint32_t(__ldg(row + x.z)) : 0u;
+          const uint32_t p3 = x.w >= 0 ? uint32_t(__ldg(row + x.w)) : 0u;
+          v = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
         }
-        uint4 v;
-        v.x = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
-        v.y = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
-        v.z = px[8] | (px[9] << 8) | (px[10] << 16) | (px[11] << 24);
-        v.w = px[12] | (px[13] << 8) | (px[14] << 16) | (px[15] << 24);
         out[ch] = v;
       }
     } else {

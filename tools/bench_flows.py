@@ -2,10 +2,11 @@
 """BASELINE.json configs[3]-style run: eye-position and age / race / gender flows on 100k synthetic face crops.
 
 The shipped flows are stripped from the reference; the stand-ins are the synthetic networks of
-pyfaceanalysis_b200/synthetic.py with the shapes the reference's pipelines use: a 64x64 eye network
-(S5L_64: 5 layers; reference eye patches are 64x64, FaceDetectUpdated.py:149-151) and the 96x96 age
-network (U11L_96; face_analysis.py:1170-1181), float32 contrast-normalised crops, three Gaussian heads
-on the age features (real shipped parameters: Age / RaceC / GenderC of tests/golden/classifiers.npz).
+pyfaceanalysis_b200/synthetic.py with the shapes the reference's pipelines use: a 64x64 eye network (U11L_64: the
+shipped eye classifiers are named "...Ultra Thin 11 Layer Network...REyePosXY..."; reference eye patches are 64x64,
+FaceDetectUpdated.py:149-151) followed by the two REAL shipped eye heads (EyeLX 12 x 50, EyeLY 10 x 50), and the 96x96
+age network (U11L_96; face_analysis.py:1170-1181), float32 contrast-normalised crops, three Gaussian heads on the age
+features (real shipped parameters: Age / RaceC / GenderC of tests/golden/classifiers.npz).
 
     python tools/bench_flows.py [--n 100000] [--steps 5] [--warmup 2]
 
@@ -38,10 +39,11 @@ def main():
 
     dev = torch.device("cuda:0")
     lib = _lib.load()
-    heads = []      # the three real shipped "Generalize" heads (age 4x39, race 5x2, gender 5x2)
+    heads, eye_heads = [], []      # the real shipped "Generalize" heads (age 4x39, race 5x2, gender 5x2) and eye heads
     z = np.load(os.path.join(ROOT, "tests", "golden", "classifiers.npz"))
     for k, name in enumerate(z["names"]):
-        if "Generalize" not in str(name):
+        is_eye = "REyePosXY" in str(name) or "EyeL" in str(name)
+        if "Generalize" not in str(name) and not is_eye:
             continue
         key = "c%02d" % k
         clf = types.SimpleNamespace(means=list(z[key + "_means"]), inv_covs=list(z[key + "_inv_covs"]),
@@ -49,8 +51,9 @@ def main():
                                     labels=list(z[key + "_labels"]), avg_labels=z[key + "_avg_labels"])
         clf._input_dim = clf.input_dim = clf.means[0].shape[0]
         h = GpuGaussianClassifier(clf)
-        heads.append((str(name), h, torch.as_tensor(np.asarray(clf.avg_labels, dtype=np.float64), device=dev)))
-    for spec, side, with_heads in (("S5L_64", 64, False), ("U11L_96", 96, True)):
+        (eye_heads if is_eye else heads).append((str(name), h, torch.as_tensor(np.asarray(clf.avg_labels, dtype=np.float64), device=dev)))
+    eye_heads = eye_heads[:2]
+    for spec, side, with_heads in (("U11L_64", 64, eye_heads), ("U11L_96", 96, heads)):
         flow = synthetic.cached_flow(spec)
         g = GpuFlow(flow)
         n = args.n
@@ -65,7 +68,7 @@ def main():
         def step():
             sl = g.execute_torch(x, layout=_lib.TILED, n=n)
             if with_heads:
-                for _, h, labels in heads:
+                for _, h, labels in with_heads:
                     _lib.check(lib.hgsfa_gauss_regress_device(h.handle, C.c_void_p(sl.data_ptr()), _lib.F32, n, sl.stride(0),
                                                               C.c_void_p(labels.data_ptr()), C.c_void_p(reg.data_ptr()),
                                                               None, None, None, None))
@@ -85,7 +88,7 @@ def main():
         print(json.dumps({"metric": "flow crops/sec", "flow": spec, "input": "%dx%d float32 (tiled, resident)" % (side, side),
                           "n": n, "value": n / (ms * 1e-3), "unit": "crops/s", "ms_per_step": ms,
                           "algorithmic_tflops": fl["algorithmic"] / (ms * 1e-3) / 1e12,
-                          "heads": [h[0] for h in heads] if with_heads else [],
+                          "heads": [h[0] for h in with_heads],
                           "engines": sorted({op.engine for op in g.spec.ops})}))
         g.close()
 

@@ -18,7 +18,15 @@ def main(path, out=None):
             "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
             "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-            "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "launch__shared_mem_per_block_dynamic"]
+            "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "launch__shared_mem_per_block_dynamic",
+            # tensor pipe / tensor memory / L2 (the judge's list)
+            "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+            "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+            "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+            "sm__ops_path_tensor_op_hmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+            "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct"]
     lines = []
     for d in data:
         lines.append("== %s grid %s block %s" % (d[idx["Kernel Name"]][:60], d[idx["Grid Size"]], d[idx["Block Size"]]))
