@@ -103,7 +103,24 @@ def spec_s5l_64():
     return dict(name="S5L_64", input_xy=(64, 64), layers=L)
 
 
-SPECS = {"U11L_64": spec_u11l_64, "U11L_96": spec_u11l_96, "tiny": spec_tiny, "S5L_64": spec_s5l_64}
+def spec_f4l_32(widths=(7, 12, 14)):
+    """Small 32x32 network with the fan-in-2 front of the ultra-thin networks (4x4 pixel fields, horizontal join,
+    vertical join, [identity, |x|^0.8] expansions) and two top layers: exercises the fused front kernel with other
+    node widths than U11L_64's (child widths padded to 8 / 16 / 32, one to four chunks per join)."""
+    f_low = ["identity", "unsigned_08expo"]
+    f_high = ["identity", "unsigned_08expo", "s10QT"]
+    w0, w1, w2 = widths
+    L = []
+    L.append(_layer((32, 32), (4, 4), (4, 4), w0, max(2, w0 // 3), f_low))        # -> 8x8
+    L.append(_layer((8, 8), (2, 1), (2, 1), w1, max(2, w1 // 3), f_low))          # H -> 4x8
+    L.append(_layer((4, 8), (1, 2), (1, 2), w2, max(2, w2 // 3), f_low))          # V -> 4x4
+    L.append(_layer((4, 4), (2, 2), (2, 2), 16, 6, f_high))                       # -> 2x2
+    L.append(_layer((2, 2), (2, 2), (1, 1), 16, 6, f_high))                       # -> 1x1
+    return dict(name="F4L_32_%d_%d_%d" % widths, input_xy=(32, 32), layers=L)
+
+
+SPECS = {"U11L_64": spec_u11l_64, "U11L_96": spec_u11l_96, "tiny": spec_tiny, "S5L_64": spec_s5l_64,
+         "F4L_32": spec_f4l_32, "F4L_32_wide": lambda: spec_f4l_32((13, 26, 27)), "F4L_32_mid": lambda: spec_f4l_32((12, 16, 30))}
 
 
 # ----------------------------------------------------------------------------------------------------

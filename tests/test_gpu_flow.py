@@ -304,3 +304,33 @@ def test_single_layer_fp16_kernel_opt_in(u11l_flow, monkeypatch):
     xf = x[:130].astype(np.float32)                 # float input: every layer but the first (no input bound) on the FP16 kernel
     _check(g, u11l_flow, xf, std=u11l_flow._train_output_std)
     g.close()
+
+
+@pytest.mark.parametrize("spec", ["F4L_32", "F4L_32_mid", "F4L_32_wide"])
+def test_fused_front_other_widths(spec, monkeypatch):
+    """The fused front is instantiated per pair of padded child widths: (8, 16), (16, 16) and (16, 32) on small 32x32
+    networks (one to four chunks per join, 16- and 32-column accumulators, subtrees split over gridDim.y), against the
+    per-layer path and the float64 oracle."""
+    import torch
+    from pyfaceanalysis_b200 import GpuFlow, synthetic
+    flow = synthetic.make_flow(spec, seed=2)
+    fused = GpuFlow(flow)
+    assert fused.fused_front, fused.front_reason
+    monkeypatch.setenv("HGSFA_FRONT", "0")
+    plain = GpuFlow(flow)
+    monkeypatch.delenv("HGSFA_FRONT")
+    std = flow._train_output_std
+    for n in (1, 130, 1500):
+        x = synthetic.synthetic_patches(n, (32, 32), 60 + n)
+        ref = onodes.flow_execute(flow, x.astype(np.float64))
+        xt = torch.as_tensor(x, device="cuda")
+        y_f = fused.execute_torch(xt).cpu().numpy().astype(np.float64)
+        y_p = plain.execute_torch(xt).cpu().numpy().astype(np.float64)
+        assert (np.abs(y_f - ref) / std).max() <= TOL, (spec, n, (np.abs(y_f - ref) / std).max())
+        assert (np.abs(y_p - ref) / std).max() <= TOL
+        assert np.array_equal(fused.execute(x), fused.execute_torch(xt).cpu().numpy().astype(np.float64))
+    fused.profile(True)
+    fused.execute(x)
+    assert [s["engine"] for s in fused.op_stats()][:3] == ["front"] * 3
+    fused.close()
+    plain.close()
