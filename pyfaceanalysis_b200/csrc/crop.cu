@@ -389,8 +389,8 @@ __global__ void __launch_bounds__(256) crop_tiled_kernel(const uint8_t* img0, in
 }
 
 // Row-major uint8 patches (what the fused flow front reads in place through its tensor map): the fast path of the detector.
-// CTA = CROP_RW windows, 256 threads.
-//   1. thread (window, axis) builds the NEAREST index table of its window in shared memory (Pillow's sequential double
+// CTA = CROP_RW windows, 256 threads, warps independent (4 windows each).
+//   1. lane (window, axis) builds the NEAREST index table of its window in shared memory (Pillow's sequential double
 //      accumulation, as in crop_index_kernel) and resolves the window's image pointer / size / angle.
 //   2. a warp takes one window at a time; a lane produces 4 consecutive pixels of a row (4 byte gathers from the L1 / L2
 //      resident image, packed into one 4-byte store; a warp's stores cover 128 contiguous bytes = 2 patch rows).
@@ -407,8 +407,10 @@ __global__ void __launch_bounds__(256) crop_rows_u8_kernel(const uint8_t* img0, 
   __shared__ double w_ang[CROP_RW];
   const int64_t w0 = int64_t(blockIdx.x) * CROP_RW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < 2 * CROP_RW) {
-    const int wl = tid >> 1, axis = tid & 1;
+  // every warp owns 4 consecutive windows and builds their tables itself (lanes 0-7 = 4 windows x 2 axes), so warps only
+  // synchronise with themselves: while one warp walks its 64-step accumulations the others gather
+  if (lane < 8) {
+    const int wl = warp * 4 + (lane >> 1), axis = lane & 1;
     const int64_t w = w0 + wl;
     const int cnt = axis ? oh : ow;
     int* tab = axis ? ys + wl * oh : xs + wl * ow;
@@ -439,12 +441,9 @@ __global__ void __launch_bounds__(256) crop_rows_u8_kernel(const uint8_t* img0, 
       }
     }
   }
-  __syncthreads();
-  // a lane produces 4 consecutive pixels: the 16 lanes of a patch row read neighbouring source bytes (few cache lines
-  // per gather instruction -- with 16 pixels per lane a warp's gathers were spread over 8 image rows and the L1
-  // wavefronts, not HBM, set the pace: 2.85 ms for 503 k windows), and a warp's 4-byte stores cover 128 contiguous bytes
+  __syncwarp();
   const int chunks_per_row = ow / 4, n_chunks = chunks_per_row * oh;
-  for (int wl = warp; wl < CROP_RW; wl += 8) {
+  for (int wl = warp * 4; wl < warp * 4 + 4; ++wl) {
     const int64_t w = w0 + wl;
     if (w >= n) break;
     const uint8_t* img = w_img[wl];
@@ -454,21 +453,43 @@ __global__ void __launch_bounds__(256) crop_rows_u8_kernel(const uint8_t* img0, 
     if (ang == 0.0 && filter == HGSFA_NEAREST) {
       const int* xt = xs + wl * ow;
       const int* yt = ys + wl * oh;
+      if (chunks_per_row <= 32 && (32 % chunks_per_row) == 0) {
+        // the usual patch widths (64: 16 chunks per row): a lane keeps ONE column chunk for the whole window -- its four
+        // source columns and their validity live in registers -- and walks down the rows, 32 / chunks_per_row rows per
+        // step: per step one table read (the row), four byte gathers, one packed 4-byte store
+        const int cc = lane % chunks_per_row, rstep = 32 / chunks_per_row;
+        const int4 x = *reinterpret_cast<const int4*>(xt + cc * 4);
+        const uint32_t mask = (x.x >= 0 ? 0xffu : 0u) | (x.y >= 0 ? 0xff00u : 0u) | (x.z >= 0 ? 0xff0000u : 0u) | (x.w >= 0 ? 0xff000000u : 0u);
+        const int x0 = max(x.x, 0), x1 = max(x.y, 0), x2 = max(x.z, 0), x3 = max(x.w, 0);
+        uint32_t* o = out + lane;
 #pragma unroll 4
-      for (int ch = lane; ch < n_chunks; ch += 32) {
-        const int r = ch / chunks_per_row, c0 = (ch - r * chunks_per_row) * 4;
-        const int y = yt[r];
-        uint32_t v = 0u;
-        if (y >= 0) {
-          const uint8_t* row = img + size_t(y) * W;
-          const int4 x = *reinterpret_cast<const int4*>(xt + c0);
-          const uint32_t p0 = x.x >= 0 ? uint32_t(__ldg(row + x.x)) : 0u;
-          const uint32_t p1 = x.y >= 0 ? uint32_t(__ldg(row + x.y)) : 0u;
-          const uint32_t p2 = x.z >= 0 ? uint32_t(__ldg(row + x.z)) : 0u;
-          const uint32_t p3 = x.w >= 0 ? uint32_t(__ldg(row + x.w)) : 0u;
-          v = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+        for (int r = lane / chunks_per_row; r < oh; r += rstep, o += 32) {
+          const int y = yt[r];
+          uint32_t v = 0u;
+          if (y >= 0) {
+            const uint8_t* row = img + size_t(y) * W;
+            v = (uint32_t(__ldg(row + x0)) | (uint32_t(__ldg(row + x1)) << 8) | (uint32_t(__ldg(row + x2)) << 16) |
+                 (uint32_t(__ldg(row + x3)) << 24)) & mask;
+          }
+          *o = v;
         }
-        out[ch] = v;
+      } else {
+#pragma unroll 4
+        for (int ch = lane; ch < n_chunks; ch += 32) {
+          const int r = ch / chunks_per_row, c0 = (ch - r * chunks_per_row) * 4;
+          const int y = yt[r];
+          uint32_t v = 0u;
+          if (y >= 0) {
+            const uint8_t* row = img + size_t(y) * W;
+            const int4 x = *reinterpret_cast<const int4*>(xt + c0);
+            const uint32_t p0 = x.x >= 0 ? uint32_t(__ldg(row + x.x)) : 0u;
+            const uint32_t p1 = x.y >= 0 ? uint32_t(__ldg(row + x.y)) : 0u;
+            const uint32_t p2 = x.z >= 0 ? uint32_t(__ldg(row + x.z)) : 0u;
+            const uint32_t p3 = x.w >= 0 ? uint32_t(__ldg(row + x.w)) : 0u;
+            v = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+          }
+          out[ch] = v;
+        }
       }
     } else {
       double cs = 1.0, sn = 0.0;
