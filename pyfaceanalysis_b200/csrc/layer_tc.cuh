@@ -41,6 +41,15 @@ constexpr int TC_EPI = HGSFA_TC_EPI;
 constexpr int TC_MMA_WARP = TC_EPI ? 8 : 4, TC_PROD_WARP = TC_MMA_WARP + 1;
 constexpr int TC_THREADS = (TC_PROD_WARP + 1) * 32;
 constexpr int TC_MAX_TW = 8;
+// ns between barrier tries of the warps that mostly wait (round 2: try_wait returns within tens of ns inside a busy CTA)
+// Measured on U11L_64 layers 3-10 (profiles/README_r02.md): 32 / 32 ns 12.41 ms, 512 / 32 12.40, 512 / 128 12.40, 2000 / 64 12.49 --
+// the re-tries only fill issue slots nobody else wants; the longer sleeps keep them out of the instruction counts.
+#ifndef HGSFA_TC_SLEEP_EPI
+#define HGSFA_TC_SLEEP_EPI 512
+#endif
+#ifndef HGSFA_TC_SLEEP_MMA
+#define HGSFA_TC_SLEEP_MMA 64
+#endif
 
 struct TcOpDev {
   int n_nodes, d_in, in_dim, out_dim, shared, twc, npc, n_runs;
@@ -370,13 +379,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t dfree_par = rd.par ^ 1u;
       for (int c = 0; c < n_chunks; ++c, rw.next()) {
         const int sw = rw.idx;
-        mbar_wait_tc(&bars[TCB_WFULL + sw], rw.par);
+        mbar_wait_tc<HGSFA_TC_SLEEP_MMA>(&bars[TCB_WFULL + sw], rw.par);
         const uint32_t wbase = smem_u32(smem + op.sm_w0 + size_t(sw) * op.sm_wstage_bytes);
         const int ksteps = (min(op.Kpad - c * TC_CK, TC_CK)) >> 3;
         for (int t = 0; t < vt; ++t, ra.next()) {
-          if (c == 0) mbar_wait_tc(&bars[TCB_DFREE + set * TC_MAX_TW + t], dfree_par);
+          if (c == 0) mbar_wait_tc<HGSFA_TC_SLEEP_MMA>(&bars[TCB_DFREE + set * TC_MAX_TW + t], dfree_par);
           const int sa = ra.idx;
-          mbar_wait_tc(&bars[TCB_AFULL + sa], ra.par);
+          mbar_wait_tc<HGSFA_TC_SLEEP_MMA>(&bars[TCB_AFULL + sa], ra.par);
           tc_fence_after();
           if (leader) {
             const uint32_t d_t = tb + uint32_t((set * op.twc + t) * op.Npad16);
@@ -410,7 +419,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int nvalid = __ldg(op.n_valid + node);
       const int col0 = __ldg(op.out_col + node) + __ldg(op.col_off + node);
       for (int t = 0; t < vt; ++t) {
-        mbar_wait_tc(&bars[TCB_DFULL + set * TC_MAX_TW + t], par);
+        mbar_wait_tc<HGSFA_TC_SLEEP_EPI>(&bars[TCB_DFULL + set * TC_MAX_TW + t], par);
         tc_fence_after();
         float* out = xout + (size_t(tile0 + t) * op.out_dim + col0) * TILE + win;
         const float clo = op.clip_lo, chi = op.clip_hi;
