@@ -11,11 +11,13 @@
 //     saturation; products are evaluated on inputs pre-scaled by 2^-s with the weights rescaled by 2^2s).
 //   * no interpreter: an A chunk is four 8-term groups whose kind / first row / count sit in a 16-byte descriptor; the
 //     group code is straight-line, means are fetched four at a time, the triangular products are unrolled at compile time.
-//   * one CTA per SM with two tile groups (8 expansion warps) sharing every weight chunk; the expansion warps store the
-//     previous node's outputs themselves (no idle epilogue warps), one node behind so that they never wait for an MMA.
-// Roles: warps 0-3 / 4-7 expansion + stores of tile group 0 / 1, warps 8 / 9 MMA issue, warp 10 producer
-// (receptive-field runs and weight chunks by cp.async.bulk).  Tensor memory per group: 2 x 64 accumulator columns +
-// 4 x 32 A columns.
+//   * one CTA per SM with two tile groups sharing every weight chunk, TWO warps per tensor-memory lane quarter and group
+//     (16 expansion warps: a pair splits the 8-term groups of every chunk and the output columns, as in the front --
+//     two in-order warps per scheduler could not hide their own latencies); the expansion warps store the previous
+//     node's outputs themselves (no idle epilogue warps), one node behind so that they never wait for an MMA.
+// Roles: warps 0-7 / 8-15 expansion + stores of tile group 0 / 1 (quarter = warp & 3, half = (warp >> 2) & 1), warps
+// 16 / 17 MMA issue, warp 18 producer (receptive-field runs and weight chunks by cp.async.bulk).  Tensor memory per
+// group: 2 x 64 accumulator columns + 4 x 32 A columns.
 #pragma once
 #include "front_tc.cuh"
 
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
   BkGroup* groups_s = reinterpret_cast<BkGroup*>(smem + 1024);              // up to 64 chunks x 4 groups
-  float* head_s = reinterpret_cast<float*>(smem + BK_SM_HEAD);              // [8 warps][2 x 64 bias | 192 mean]
+  float* head_s = reinterpret_cast<float*>(smem + BK_SM_HEAD);              // [16 warps][2 x 64 bias | 192 mean]
   uint8_t* wring = smem + BK_SM_W;
   uint8_t* xring = smem + smem_x0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -63,8 +65,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1)
     for (int i = 0; i < BK_NW; ++i) { mbar_init(&bars[BKB_WFULL + i], 1); mbar_init(&bars[BKB_WFREE + i], 2); }
     for (int g = 0; g < 2; ++g) {
       uint64_t* gb = bars + BKB_G + g * BKB_GSTRIDE;
-      for (int i = 0; i < BK_NA; ++i) { mbar_init(&gb[BKB_AFULL + i], 4); mbar_init(&gb[BKB_AFREE + i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&gb[BKB_DFULL + i], 1); mbar_init(&gb[BKB_XFULL + i], 1); mbar_init(&gb[BKB_XFREE + i], 4); }
+      for (int i = 0; i < BK_NA; ++i) { mbar_init(&gb[BKB_AFULL + i], BK_EXP_WARPS / 2); mbar_init(&gb[BKB_AFREE + i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&gb[BKB_DFULL + i], 1); mbar_init(&gb[BKB_XFULL + i], 1); mbar_init(&gb[BKB_XFREE + i], BK_EXP_WARPS / 2); }
     }
     mbar_fence_init();
   }
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1)
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
 
-  if (warp == 10) {
+  if (warp == BK_EXP_WARPS + 2) {
     // ================================ producer ================================
     if (lane == 0) {
       Ring rw(BK_NW), rx(bd.nstx);
@@ -104,9 +106,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1)
       }
     }
     __syncwarp();
-  } else if (warp >= 8) {
+  } else if (warp >= BK_EXP_WARPS) {
     // ================================ MMA issue (one warp per tile group) ================================
-    const int g = warp - 8;
+    const int g = warp - BK_EXP_WARPS;
     uint64_t* gb = bars + BKB_G + g * BKB_GSTRIDE;
     const bool leader = elect_one();
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0) + uint32_t(g * BK_GCOLS);
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1)
     }
   } else {
     // ================================ expansion + stores (thread = window) ================================
-    const int g = warp >> 2;
+    const int g = warp >> 3, half = (warp >> 2) & 1;
     const int win = tid & (TILE - 1);
     uint64_t* gb = bars + BKB_G + g * BKB_GSTRIDE;
     const uint32_t lane_base = tbase + (uint32_t((warp & 3) * 32) << 16) + uint32_t(g * BK_GCOLS);
@@ -158,12 +160,12 @@ __global__ void __launch_bounds__(BK_THREADS, 1)
       float* out = xout + (size_t(tile) * bd.out_dim + __ldg(bd.out_col + node)) * TILE + win;
       const float* bias = bias_w + slot * 64;
 #pragma unroll 1
-      for (int n0 = 0; n0 < bd.nn; n0 += 16) {
-        uint32_t r[16];
-        tmem_ld_cols<16>(lane_base + uint32_t(BK_COL_ACC + 64 * slot + n0), r);
+      for (int n0 = 8 * half; n0 < bd.nn; n0 += 16) {          // this warp's 8 of every 16 columns
+        uint32_t r[8];
+        tmem_ld8(lane_base + uint32_t(BK_COL_ACC + 64 * slot + n0), r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < 16; k += 4) {
+        for (int k = 0; k < 8; k += 4) {
           if (n0 + k < nv) {
             const float4 b = *reinterpret_cast<const float4*>(bias + n0 + k);
             const float y0 = fminf(fmaxf(fmaf(__uint_as_float(r[k + 0]), bd.scale, b.x), bd.clo), bd.chi);
@@ -200,10 +202,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1)
       }
 #pragma unroll 1
       for (int c = 0; c < n_chunks; ++c, rw.next()) {
-        uint32_t hi[16], lo[16];
+        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          const BkGroup gr = groups_s[c * 4 + gi];
+        for (int gi = 0; gi < 2; ++gi) {
+          const BkGroup gr = groups_s[c * 4 + 2 * half + gi];      // this warp's two 8-term groups of the chunk
           float v[8];
           if (gr.kind == BK_TRI) {
             bk_tri_group<BK_TRI_N, 0>(xc, gr.tri, v);
@@ -232,9 +234,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1)
         }
         fr_wait(&gb[BKB_AFREE + ra.idx], ra.par ^ 1u);
         tc_fence_after();
-        const uint32_t col = lane_base + uint32_t(BK_COL_A + 32 * ra.idx);
-        tmem_st16(col, hi);
-        tmem_st16(col + 16, lo);
+        const uint32_t col = lane_base + uint32_t(BK_COL_A + 32 * ra.idx + 8 * half);
+        tmem_st8(col, hi);
+        tmem_st8(col + 16, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();

@@ -37,10 +37,11 @@ struct Run;
 constexpr int BK_NW = 6;                  // weight-ring stages
 constexpr int BK_NA = 4;                  // A-ring stages per group
 constexpr int BK_WSTAGE = FR_HEAD + 32 * 64 * 4;
-constexpr int BK_THREADS = 11 * 32;
+constexpr int BK_EXP_WARPS = 16;          // two tile groups x four lane quarters x two halves
+constexpr int BK_THREADS = (BK_EXP_WARPS + 3) * 32;
 constexpr int BK_COL_ACC = 0, BK_COL_A = 128, BK_GCOLS = 256;
 constexpr int BK_TRI_N = 10;              // triangular products over 10 centred inputs (cuicuilco's s10 selectors)
-constexpr int BK_SM_HEAD = 1024 + 4096, BK_HEAD_WARP = 128 + 192, BK_SM_W = BK_SM_HEAD + 8 * BK_HEAD_WARP * 4;
+constexpr int BK_SM_HEAD = 1024 + 4096, BK_HEAD_WARP = 128 + 192, BK_SM_W = BK_SM_HEAD + BK_EXP_WARPS * BK_HEAD_WARP * 4;
 constexpr int BK_SM_X = BK_SM_W + BK_NW * BK_WSTAGE;
 enum { BKB_WFULL = 0, BKB_WFREE = BK_NW, BKB_G = 2 * BK_NW, BKB_AFULL = 0, BKB_AFREE = BK_NA, BKB_DFULL = 2 * BK_NA,
        BKB_XFULL = 2 * BK_NA + 2, BKB_XFREE = 2 * BK_NA + 4, BKB_GSTRIDE = 2 * BK_NA + 6, BKB_COUNT = 2 * BK_NW + 2 * BKB_GSTRIDE };

@@ -51,6 +51,10 @@ constexpr int TC_MAX_TW = 8;
 #define HGSFA_TC_SLEEP_MMA 64
 #endif
 
+#ifndef HGSFA_TC_MINB
+#define HGSFA_TC_MINB 1     // resident CTAs per SM the register allocation is sized for
+#endif
+
 struct TcOpDev {
   int n_nodes, d_in, in_dim, out_dim, shared, twc, npc, n_runs;
   int K, Kpad, Npad16, n_chunks, n_terms, n_segs;
@@ -277,7 +281,7 @@ __device__ __forceinline__ void tc_seg_tri(const IN_T* xr, const float* mr, int 
 }
 
 template <typename IN_T>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
     layer_tc_kernel(const TcOpDev op, const IN_T* __restrict__ xin, float* __restrict__ xout, int64_t ntiles) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
