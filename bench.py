@@ -252,9 +252,16 @@ def run_detect(args, rank, world, local_rank, dev, barrier, dist):
     from pyfaceanalysis_b200.cascade import FaceDetector
     cfg = DETECT_CONFIGS[args.detect_config]
     m = cm.cached_models(spec=FLOW_SPEC)
-    flows, heads = {}, {}
-    nets = [None if f is None else flows.setdefault(id(f), GpuFlow(f, device=local_rank)) for f in m["networks"]]
-    clfs = [None if c is None else heads.setdefault(id(c), GpuGaussianClassifier(c, device=local_rank)) for c in m["classifiers"]]
+    all_flows = []
+
+    def model_set():
+        """One set of device objects (plans with their workspaces, heads): a lane owns its own, nothing is shared."""
+        flows, heads = {}, {}
+        nets = [None if f is None else flows.setdefault(id(f), GpuFlow(f, device=local_rank)) for f in m["networks"]]
+        clfs = [None if c is None else heads.setdefault(id(c), GpuGaussianClassifier(c, device=local_rank)) for c in m["classifiers"]]
+        all_flows.extend(flows.values())
+        return nets, clfs
+    nets, clfs = model_set()
     n_img = args.detect_images or cfg["images"]
     total = n_img * world
     mine = shard.image_shard(total, rank, world)                     # round robin over the global image list
@@ -272,24 +279,83 @@ def run_detect(args, rank, world, local_rank, dev, barrier, dist):
         _, tr0 = cal.detect([cal_img], smallest_face=cfg["smallest_face"], return_trace=True)
         sc = tr0["disc_scores"].get(name)
         cut[int(name[-1])] = float(np.nanquantile(sc, frac)) if sc is not None and len(sc) else 0.0
-    det = FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=cut, header_eye=m["header_eye"], device=local_rank)
+    # Throughput mode of the detector: `lanes` independent FaceDetector instances, each driven by its own host thread on
+    # its own CUDA stream, take alternate batches, so that the host part of one batch (launch loop, eye bookkeeping, purge)
+    # runs under the kernels of the other lane's batch; the pinned-host -> device copy of a lane's next batch runs on a copy
+    # stream, and the gather of the detection lists (host objects, gloo) on a helper thread, in batch order.  Every batch is
+    # still uploaded, processed and gathered exactly once per step, all inside the timed region.
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    n_lanes = max(1, args.detect_lanes)
+    lanes = []
+    for j in range(n_lanes):
+        ln_nets, ln_clfs = (nets, clfs) if j == 0 else model_set()
+        lanes.append(dict(det=FaceDetector(m["header"], m["network_types"], ln_nets, ln_clfs, cut_offs_face=cut,
+                                           header_eye=m["header_eye"], device=local_rank),
+                          stream=torch.cuda.Stream(dev), up=torch.cuda.Stream(dev)))
+    det = lanes[0]["det"]
+    gather_group = dist.new_group(backend="gloo") if world > 1 else None
+    pool = ThreadPoolExecutor(1)
 
-    def step(bench=None):
-        imgs = [h.to(dev, non_blocking=True) for h in host]
-        if cfg["prescale"]:
-            imgs = det.prescale(imgs)
-        local, tr = det.detect(imgs, smallest_face=cfg["smallest_face"], return_trace=True, benchmark=bench)
-        allr = shard.gather_detections(local, mine, total)            # per-image lists, host objects, every rank
-        return allr, tr
+    def upload(lane):
+        with torch.cuda.stream(lane["up"]):
+            imgs = [h.to(dev, non_blocking=True) for h in host]
+            ev = torch.cuda.Event()
+            ev.record(lane["up"])
+        return imgs, ev
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        allr, tr = step()
+    def lane_loop(j, k, n_steps, out, done, bench, errors):
+        """Lane j of k active lanes: batches j, j + k, ... on this thread and this lane's stream."""
+        lane = lanes[j]
+        try:
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(lane["stream"]):
+                mine_steps = list(range(j, n_steps, k))
+                nxt = upload(lane) if mine_steps else None
+                for pos, i in enumerate(mine_steps):
+                    imgs, ev = nxt
+                    lane["stream"].wait_event(ev)
+                    for t in imgs:
+                        t.record_stream(lane["stream"])
+                    nxt = upload(lane) if pos + 1 < len(mine_steps) else None
+                    if cfg["prescale"]:
+                        imgs = lane["det"].prescale(imgs)
+                    out[i] = lane["det"].detect(imgs, smallest_face=cfg["smallest_face"], return_trace=True, benchmark=bench)
+                    done[i].set()
+        except BaseException as e:          # noqa: BLE001 -- re-raised by run()
+            errors.append(e)
+            for d in done:
+                d.set()
+
+    def run(n_steps, bench=None, use_lanes=None):
+        k = n_lanes if use_lanes is None else use_lanes
+        out, done, errors = [None] * n_steps, [threading.Event() for _ in range(n_steps)], []
+        threads = [threading.Thread(target=lane_loop, args=(j, k, n_steps, out, done, bench, errors)) for j in range(k)] if k > 1 else []
+        for t in threads:
+            t.start()
+        if k == 1:
+            lane_loop(0, 1, n_steps, out, done, bench, errors)
+        pending, allr = None, None
+        for i in range(n_steps):                                       # gathers in batch order: same order on every rank
+            done[i].wait()
+            if errors:
+                break
+            if pending is not None:
+                allr = pending.result()
+            pending = pool.submit(shard.gather_detections, out[i][0], mine, total, gather_group)
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        allr = pending.result()
+        return allr, out[-1][1]
+
+    steps = max(n_lanes, min(args.steps, 6) // n_lanes * n_lanes)      # a multiple of the lanes
+    allr, tr = run(max(n_lanes, min(args.warmup, 2) * n_lanes))
     torch.cuda.synchronize(dev)
     barrier()
-    steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
-    for _ in range(steps):
-        allr, tr = step()
+    allr, tr = run(steps)
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -297,7 +363,8 @@ def run_detect(args, rank, world, local_rank, dev, barrier, dist):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item()) / steps
     stage_bench = _StageTimes()
-    step(stage_bench)                                                 # one more, untimed, with device times per label
+    run(1, stage_bench, use_lanes=1)                                  # one more, untimed, alone: device times per label
+    pool.shutdown()
     res = None
     if rank == 0:
         peaks = _peaks()
@@ -312,7 +379,11 @@ def run_detect(args, rank, world, local_rank, dev, barrier, dist):
                                                                                cfg["smallest_face"], "NEAREST prescale to <= 1000 px on the device"
                                                                                if cfg["prescale"] else "no prescale (--image_prescaling=0)", FLOW_SPEC),
                           "sharding": "images round robin over ranks (shard.image_shard), detection lists gathered with "
-                                      "all_gather_object (shard.gather_detections)"},
+                                      "all_gather_object on a gloo group (shard.gather_detections)",
+                          "lanes": n_lanes,
+                          "overlap": "%d detector instances on their own streams and host threads take alternate batches; upload of a "
+                                     "lane's next batch on a copy stream, gather of the detection lists on a helper thread; "
+                                     "stage_ms is one batch alone on one lane" % n_lanes},
                "windows_per_gpu": int(tr["n_windows"]), "stage_counts": [int(c) for c in tr["stage_counts"]],
                "detections_total": int(sum(len(o) for o in allr)), "host_syncs_per_batch": int(tr["host_syncs"]),
                "calibrated_cut_offs": cut,
@@ -337,7 +408,7 @@ def run_detect(args, rank, world, local_rank, dev, barrier, dist):
             res["cpu_baseline"] = {"value": 1.0 / cdt, "unit": "images/s", "cores": threads, "nproc": os.cpu_count(), "kind": "port",
                                    "sample": "1 image (%d windows), float64 numpy oracle of the reference loop, %.1f s"
                                              % (int(tr["n_windows"]) // n_img, cdt)}
-    for g in flows.values():
+    for g in all_flows:
         g.close()
     return res
 
@@ -408,6 +479,7 @@ def main():
     ap.add_argument("--detect-config", type=int, default=2, choices=sorted(DETECT_CONFIGS), help="2: 64 x 1920x1080 prescaled; "
                     "4: 21 x 3840x2160 without prescale (~1e6 windows per GPU)")
     ap.add_argument("--detect-images", type=int, default=0, help="images per GPU (0 = the config's)")
+    ap.add_argument("--detect-lanes", type=int, default=2, help="detector instances (streams + host threads) per GPU taking alternate batches")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)

@@ -66,6 +66,21 @@ def approximate_eye_boxes(boxes, angles):
     return eyes, box(eyes[:, 0], eyes[:, 1]), box(eyes[:, 2], eyes[:, 3])
 
 
+def group_confidences(cf, ok, grp):
+    """The reference's confidence bookkeeping of the eye stage (``FaceDetectUpdated.py:1011-1017, 1036-1041``):
+    ``curr_confidence`` of a (image, scale) group is NOT filtered by ``eye_xy_too_far``, so survivor j of a group reports
+    the confidence of that group's face j.  cf: (n,), ok: (n,) bool, grp: (n, k) group keys, equal keys consecutive.
+    One gather instead of a Python loop over the faces (hundreds per batch)."""
+    n = len(cf)
+    if n == 0:
+        return np.empty(0)
+    grp = np.asarray(grp).reshape(n, -1)
+    starts = np.flatnonzero(np.concatenate([[True], np.any(grp[1:] != grp[:-1], axis=1)]))
+    k_ok = np.add.reduceat(np.asarray(ok, dtype=np.int64), starts)
+    first = np.cumsum(k_ok) - k_ok                         # output position of each group's first survivor
+    return np.asarray(cf)[np.repeat(starts - first, k_ok) + np.arange(int(k_ok.sum()))]
+
+
 def purge_detections(det, weight_confidences_by_area=True):
     """``purgue_detected_faces_angles_eyes_confidence`` (reference ``face_analysis.py:186-221``); rows are
     [x0, y0, x1, y1, angle, eye_l_x, eye_l_y, eye_r_x, eye_r_y, confidence].  Dozens of rows: stays on the host."""
@@ -152,7 +167,7 @@ class FaceDetector(object):
         self.attributes = attributes
         # windows above which a Disc stage is followed by a compaction (one host round trip); below it discarded windows
         # simply ride along
-        self.lazy_threshold = int(self.cfg.get("lazy_threshold", 32768))
+        self.lazy_threshold = int(self.cfg.get("lazy_threshold", os.environ.get("HGSFA_LAZY_THRESHOLD", 4096)))
         # eye stage: network_types[n_stages] = EyeLX, [n_stages + 1] = EyeLY (same flow file, two heads)
         self.header_eye = tuple(header_eye) if header_eye is not None else None
         self.eye_net = None
@@ -442,18 +457,7 @@ class FaceDetector(object):
                                    (eyesR_box[:, 0:2] + eyesR_box[:, 2:4]) / 2.0], axis=1)[ok]
             # reference quirk kept (FaceDetectUpdated.py:1011-1017, 1036-1041): curr_confidence is not filtered by
             # eye_xy_too_far, so survivor j of a (scale, image) group reports the confidence of that group's face j
-            cf_out = np.empty(int(ok.sum()))
-            pos = 0
-            grp = np.stack([im_of, scale_of], axis=1)
-            start = 0
-            while start < n:
-                stop = start
-                while stop < n and (grp[stop] == grp[start]).all():
-                    stop += 1
-                k_ok = int(ok[start:stop].sum())
-                cf_out[pos:pos + k_ok] = cf[start:start + k_ok]
-                pos += k_ok
-                start = stop
+            cf_out = group_confidences(cf, ok, np.stack([im_of, scale_of], axis=1))
             boxes, ang, im_of, cf = boxes[ok], ang[ok], im_of[ok], cf_out
             n = len(boxes)
         else:

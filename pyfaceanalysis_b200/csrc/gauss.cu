@@ -165,7 +165,9 @@ int launch_gauss(hgsfa_gauss_t h, const XT* x, int64_t n, int64_t ld, const doub
   const unsigned grid = (unsigned)ceil_div(n, GT);
 #define HG_GAUSS(DM)                                                                                            \
   do {                                                                                                          \
-    HG_CUDA(cudaFuncSetAttribute(gauss_kernel<DM, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    /* the limit is per function and device, not per launch: always the full budget, so that concurrent callers with    \
+       classifiers of different sizes (one host thread per stream) cannot lower it under each other's launches */       \
+    HG_CUDA(cudaFuncSetAttribute(gauss_kernel<DM, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
     gauss_kernel<DM, XT><<<grid, GT, smem, st>>>(x, n, ld, D, C, group, (const double*)h->means.p,             \
                                                  (const double*)h->inv_covs.p, (const double*)h->consts.p,     \
                                                  (const double*)h->priors.p, labels, value, stdv, winner, probs); \

@@ -65,3 +65,30 @@ def test_clock_sampler_window(tmp_path):
         out = s.stop(t, t + 0.5)
         assert out["sm_mhz"] == expect[0] and out["samples"] == expect[1] and out["reasons"] == expect[2]
         assert out["sm_max_mhz"] == 1965.0 and (expect[3] is None or out["window"] == expect[3])
+
+
+def test_group_confidences_matches_the_reference_loop():
+    """Eye stage bookkeeping (FaceDetectUpdated.py:1011-1017, 1036-1041): within a (image, scale) group the survivors take
+    the confidences of the group's FIRST faces, whichever faces were dropped."""
+    from pyfaceanalysis_b200.cascade import group_confidences
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 2, 7, 64, 500):
+        cf = rng.random(n)
+        ok = rng.random(n) > 0.3
+        im = np.sort(rng.integers(0, 5, n))
+        sc = np.zeros(n, dtype=np.int64)
+        for k in np.unique(im):                     # scales ascending inside an image, as the pyramid enumerates them
+            sc[im == k] = np.sort(rng.integers(0, 4, int((im == k).sum())))
+        grp = np.stack([im, sc], axis=1)
+        want = np.empty(int(ok.sum()))
+        pos = start = 0
+        while start < n:                            # the reference's per-group slices, written as a loop
+            stop = start
+            while stop < n and (grp[stop] == grp[start]).all():
+                stop += 1
+            k_ok = int(ok[start:stop].sum())
+            want[pos:pos + k_ok] = cf[start:start + k_ok]
+            pos += k_ok
+            start = stop
+        got = group_confidences(cf, ok, grp)
+        assert got.shape == want.shape and np.array_equal(got, want)
