@@ -378,6 +378,46 @@ def test_lazy_compaction_is_invisible(monkeypatch):
             assert np.array_equal(a, b)
 
 
+def test_two_detector_lanes_on_two_threads():
+    """Throughput mode (bench.py run_detect): two FaceDetector instances with their own device objects,
+    each on its own stream and host thread, give exactly the serial results.  Regression test of the shared-memory-limit
+    race of the Gaussian head launch (classifiers of different sizes launched concurrently)."""
+    import threading
+    import torch
+    from pyfaceanalysis_b200.cascade import FaceDetector
+    m = cm.cached_models()
+    images = [[cm.test_scene(seed)[0] for seed in pair] for pair in ((5, 8), (6, 7))]
+    lanes = []
+    for _ in range(2):
+        nets, clfs = _gpu_models(m)
+        lanes.append((FaceDetector(m["header"], m["network_types"], nets, clfs, cut_offs_face=CUT, header_eye=m["header_eye"]),
+                      torch.cuda.Stream()))
+    serial = [lanes[j][0].detect(images[j], smallest_face=0.2) for j in range(2)]
+    torch.cuda.synchronize()
+    results, errors = [[], []], []
+
+    def loop(j):
+        try:
+            det, stream = lanes[j]
+            with torch.cuda.stream(stream):
+                for _ in range(6):
+                    results[j].append(det.detect(images[j], smallest_face=0.2))
+        except BaseException as e:      # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=loop, args=(j,)) for j in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for j in range(2):
+        assert len(results[j]) == 6
+        for got in results[j]:
+            assert len(got) == len(serial[j])
+            for a, b in zip(got, serial[j]):
+                assert np.array_equal(a, b)
+
+
 def test_benchmark_labels_and_result_lines():
     """benchmark= receives device times under the reference's labels (FaceDetectUpdated.py:691,711,724,760); the text
     writer reproduces the result line format (FaceDetectUpdated.py:1258-1278)."""

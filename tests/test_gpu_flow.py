@@ -334,3 +334,39 @@ def test_fused_front_other_widths(spec, monkeypatch):
     assert [s["engine"] for s in fused.op_stats()][:3] == ["front"] * 3
     fused.close()
     plain.close()
+
+
+def test_full_size_batch_properties(u11l_flow):
+    """configs[1] at BASELINE.json's full size (1 048 576 windows x 4096 uint8, resident in HBM), through properties that
+    do not need the slow oracle at that size:
+      * position independence: the batch is 8 192 distinct windows replicated 128 times in a random order -- every copy
+        of a window must give bit-identical features whatever its tile, lane, chunk or CTA;
+      * shard invariance (shard.window_shard): the features of a tile-aligned slice computed alone are
+        bit-identical to the same rows of the full batch;
+      * parity of a sample of the distinct windows against the float64 oracle within TOL x std."""
+    import torch
+    from pyfaceanalysis_b200 import GpuFlow, shard, synthetic
+    n_distinct, n = 8192, 1 << 20
+    base = torch.from_numpy(np.ascontiguousarray(synthetic.synthetic_patches(n_distinct, (64, 64), 77).astype(np.uint8))).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    src = torch.randperm(n, device="cuda", generator=gen) % n_distinct      # window i is a copy of base[src[i]]
+    x = base[src]
+    assert x.shape == (n, 4096) and x.dtype == torch.uint8
+    g = GpuFlow(u11l_flow)
+    assert g.fused_front
+    y = g.execute_torch(x).clone()
+    assert y.shape == (n, 60) and bool(torch.isfinite(y).all())
+    # one representative per distinct window (its first occurrence), then every row against its representative
+    first = torch.full((n_distinct,), n, dtype=torch.int64, device="cuda").scatter_reduce(
+        0, src, torch.arange(n, device="cuda"), reduce="amin")
+    rep = y[first]
+    assert bool((y.view(torch.int32) == rep[src].view(torch.int32)).all())
+    for rank, world in ((3, 8), (1, 2)):
+        a, b = shard.window_shard(n, rank, world)
+        part = g.execute_torch(x[a:b]).clone()
+        assert bool((part.view(torch.int32) == y[a:b].view(torch.int32)).all())
+    sample = np.arange(0, n_distinct, 64)
+    ref = onodes.flow_execute(u11l_flow, base[sample].cpu().numpy().astype(np.float64))
+    err = np.abs(rep[sample].double().cpu().numpy() - ref) / u11l_flow._train_output_std
+    assert err.max() <= TOL, "max err/std %.3g" % err.max()
+    g.close()
