@@ -358,6 +358,26 @@ def test_config3_fhd_image_with_device_prescale(engine, monkeypatch):
     assert np.array_equal(many[1].cpu().numpy(), np.asarray(Image.fromarray(full[::-1].copy(), "L").resize((1000, 562), Image.NEAREST)))
 
 
+def test_4k_image_without_prescale(monkeypatch):
+    """BASELINE configs[4]'s image size and --image_prescaling=0: 3840 x 2160 read in place, boxes from 257 to 2 454 pixels
+    a side (the largest NEAREST down-sampling the crop kernel sees; the biggest boxes hang over the image border).
+    smallest_face 0.1 -> 1 729 windows, so that the oracle's statement-by-statement loop (Pillow crops, float64 controller,
+    driven with the GPU flow and head) finishes in seconds; at smallest_face 0.02 (48 089 windows) its per-window Python
+    costs tens of minutes -- that size runs in bench.py --detect-config 4."""
+    rng = np.random.default_rng(404)
+    faces = [(rng.uniform(400, 3400), rng.uniform(400, 1800), rng.uniform(300, 1200), rng.uniform(-10, 10)) for _ in range(5)]
+    img = cm.render_scene(2160, 3840, faces, 909)
+    m, det, nets, clfs = _u11l_detector("auto", monkeypatch)
+    got, trace = det.detect([img], smallest_face=0.1, return_trace=True)
+    assert trace["n_windows"] == 1729
+    hyb, trh = _hybrid_run(img, m, nets, clfs, 0.1)
+    print("stage counts", trace["stage_counts"].tolist(), "detections", len(got[0]))
+    assert np.array_equal(trace["stage_counts"], trh["stage_counts"])
+    assert trace["raw"][0].shape == trh["raw"].shape
+    assert np.allclose(trace["raw"][0][:, [0, 1, 2, 3, 4, 9]], trh["raw"][:, [0, 1, 2, 3, 4, 9]], rtol=0, atol=1e-9)
+    assert np.allclose(trace["raw"][0], trh["raw"], rtol=0, atol=1e-4) and np.allclose(got[0], hyb, rtol=0, atol=1e-4)
+
+
 def test_lazy_compaction_is_invisible(monkeypatch):
     """Discarded windows may ride along until the next compaction (cascade.py): forcing a compaction after every Disc
     stage, or none before the end, gives the same detections, counts and order."""
