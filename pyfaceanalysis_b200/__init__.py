@@ -8,6 +8,8 @@ Public surface (mirrors the reference's objects):
     load_network_subimages(...) / extract_subimages(...)  # face_analysis.load_network_subimages
     load_obj(base_dir, base_filename)                     # Cache.load_obj_from_cache
     AttributeEstimator(net, age, race, gender).estimate   # estimate_age_race_gender on normalised crops
+    cascade.FaceDetector(...).detect(images)              # the per-image loop of FaceDetectUpdated.py, batched
+    batch.run_batch(detector, batch_filename)             # python FaceDetect.py --batch=batch_filename
 
 All compute goes through ``libhgsfa.so`` (``include/hgsfa.h``); there is no CPU fallback.
 """
