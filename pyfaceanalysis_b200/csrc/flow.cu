@@ -298,7 +298,8 @@ int launch_layer_tc(hgsfa_plan_s* pl, OpHost& op, const void* xin, float* xout, 
   const size_t smem = layout_tc(d, d.n_segs, (int)sizeof(IN_T));
   HG_CHECK(smem <= op.tc_smem[v], "tensor-core layer launch needs %zu bytes of shared memory, reserved %zu", smem, op.tc_smem[v]);
   dim3 grid((unsigned)ceil_div(ntiles, d.twc), (unsigned)ceil_div(d.n_nodes, d.npc));
-  layer_tc_kernel<IN_T><<<grid, TC_THREADS, smem, st>>>(d, static_cast<const IN_T*>(xin), xout, ntiles);
+  if (d.f16) layer_tc_kernel<IN_T, true><<<grid, TC_THREADS, smem, st>>>(d, static_cast<const IN_T*>(xin), xout, ntiles);
+  else layer_tc_kernel<IN_T, false><<<grid, TC_THREADS, smem, st>>>(d, static_cast<const IN_T*>(xin), xout, ntiles);
   pl->launches++;
   HG_CUDA(cudaGetLastError());
   return 0;
@@ -535,6 +536,69 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
           chunk_seg[t.n_chunks] = (int32_t)tsegs.size();
         }
         t.n_segs = (int)tsegs.size();
+        // ---- FP16 pieces instead of TF32 pieces (layer_tc.cuh, F16 = true; opt-in, HGSFA_TC_F16=1) where every operand
+        // provably fits FP16's range: float inputs bounded by the previous op's saturation, term kinds with a known bound,
+        // operands of products pre-scaled.  Per unit of K the kind::f16 MMA holds the tensor pipe 3-4x shorter at N = 48-64,
+        // a weight chunk is half the bytes and the accuracy is the same (22 significant bits per operand) -- but measured on
+        // layers 3-10 of U11L_64 it is no faster (12.9 vs 12.7 ms per 1 Mi windows, profiles/README_r02.md item 13): neither
+        // the tensor pipe nor the weight stream is what holds these layers, so 3xTF32 (no range conditions) stays the default.
+        t.f16 = 0;
+        t.scale = 1.0f;
+        t.prod_scale = 1.0f;
+        double f16_wmul = 1.0, f16_prod_w = 1.0;
+        std::vector<uint8_t> is_prod(dp.K, 0);
+        {
+          const char* env = getenv("HGSFA_TC_F16");
+          bool ok = env && env[0] == '1' && o > 0;
+          double bound_c = 0.0;
+          if (ok) {
+            const OpDev& prev = pl->ops[o - 1].dev;
+            const double bound_in = std::max(std::fabs((double)prev.clip_lo), std::fabs((double)prev.clip_hi));
+            double max_mean = 0.0;
+            for (int w = 0; w < n_w; ++w)
+              for (int i = 0; i < d.d_in; ++i) max_mean = std::max(max_mean, std::fabs((double)params[size_t(w) * d.param_floats + i]));
+            bound_c = bound_in + max_mean;
+            ok = std::isfinite(bound_c) && bound_c > 0.0 && bound_c <= 32768.0;
+          }
+          for (const Seg& pc : tsegs) {
+            if (!ok) break;
+            switch (pc.op) {
+              case OP_ID: case OP_ABS: case OP_CLIP: break;
+              case OP_ABSPOW: case OP_SGNPOW:
+                ok = pc.p > 0.f && (pc.p <= 1.f || std::pow(std::max(1.0, bound_c), (double)pc.p) <= 32768.0);
+                break;
+              case OP_MUL: case OP_TRI: break;                      // operands pre-scaled below
+              case OP_MUL3: ok = bound_c * bound_c * bound_c <= 32768.0; break;
+              default: ok = false; break;
+            }
+          }
+          double max_w = 0.0;
+          int prod_shift = 0;
+          if (ok) {
+            while (bound_c / double(1 << prod_shift) > 128.0 && prod_shift < 12) ++prod_shift;   // products stay below 2^14
+            f16_prod_w = std::ldexp(1.0, 2 * prod_shift);
+            for (const Seg& pc : tsegs)
+              if (pc.op == OP_TRI || pc.op == OP_MUL)
+                for (int q = 0; q < pc.kind; ++q) is_prod[pc.pad1 + q] = 1;
+            for (int w = 0; w < n_w; ++w)
+              for (int k = 0; k < dp.K; ++k)
+                for (int n = 0; n < std::min(dp.Npad, t.Npad16); ++n)
+                  max_w = std::max(max_w, std::fabs((double)params[size_t(w) * d.param_floats + dp.w_off + size_t(k) * dp.Npad + n]) *
+                                              (is_prod[k] ? f16_prod_w : 1.0));
+            ok = max_w > 0.0 && std::isfinite(max_w);
+          }
+          if (ok) {
+            const int tpow = (int)std::floor(std::log2(16384.0 / max_w));      // weights stored times 2^tpow: |w| <= 2^14
+            t.f16 = 1;
+            t.scale = (float)std::ldexp(1.0, -tpow);
+            t.prod_scale = (float)std::ldexp(1.0, -prod_shift);
+            f16_wmul = std::ldexp(1.0, tpow);
+            t.wchunk_floats = TC_CK * t.Npad16;                                // two FP16 images = half the bytes
+            const int cols16 = t.nd * t.twc * t.Npad16 + t.na * TC_CK;         // an A stage is TC_CK columns (two terms each)
+            t.tmem_cols = 32;
+            while (t.tmem_cols < cols16) t.tmem_cols *= 2;
+          }
+        }
         // head = x_mean | bias;  weight chunks = TF32 hi image | lo image, canonical K-major core matrices
         const size_t head_bytes = size_t(n_w) * t.head_floats * 4;
         const size_t wimg_bytes = size_t(n_w) * t.n_chunks * t.wchunk_floats * 4;
@@ -557,6 +621,16 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
             float* img = wimg + (size_t(w) * t.n_chunks + c) * t.wchunk_floats;
             for (int n = 0; n < std::min(dp.Npad, t.Npad16); ++n) {
               const float wv = pw[dp.w_off + size_t(k) * dp.Npad + n];
+              if (t.f16) {
+                // canonical K-major core matrices of 8 rows x 8 halves; hi image, then lo image
+                __half* hi16 = reinterpret_cast<__half*>(img);
+                const size_t off = (size_t((kk >> 3) * nb8 + (n >> 3)) * 8 + (n & 7)) * 8 + (kk & 7);
+                const double ws = double(wv) * f16_wmul * (is_prod[k] ? f16_prod_w : 1.0);
+                const __half h = __float2half_rn(float(ws));
+                hi16[off] = h;
+                hi16[size_t(TC_CK) * t.Npad16 + off] = __float2half_rn(float(ws - double(__half2float(h))));
+                continue;
+              }
               const float hi = tf32_rn(wv);
               const size_t off = (size_t((kk >> 2) * nb8 + (n >> 3)) * 8 + (n & 7)) * 4 + (kk & 3);
               img[off] = hi;
@@ -739,8 +813,10 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
     size_t& cur_tc = dev_max_tc[device & 63];
     size_t& cur_smem = dev_max_smem[device & 63];
     if (max_tc > cur_tc) {
-      if (cudaFuncSetAttribute(layer_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess ||
-          cudaFuncSetAttribute(layer_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess)
+      if (cudaFuncSetAttribute(layer_tc_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess ||
+          cudaFuncSetAttribute(layer_tc_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess ||
+          cudaFuncSetAttribute(layer_tc_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess ||
+          cudaFuncSetAttribute(layer_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_tc) != cudaSuccess)
         return plan_fail(pl, "cannot reserve %zu bytes of dynamic shared memory for the tensor-core kernel", max_tc);
       cur_tc = max_tc;
     }
@@ -996,7 +1072,7 @@ extern "C" int hgsfa_plan_op_stats(hgsfa_plan_t pl, int64_t capacity, double* ms
   for (size_t o = 0; o < pl->ops.size(); ++o) {
     if (ms) ms[o] = pl->op_ms[o];
     // 2: fused front (uint8 inputs; time booked on op 0), 3: single-layer FP16-split kernel (float inputs)
-    if (engine) engine[o] = (pl->front_ok && o < 3) ? 2 : (pl->ops[o].back ? 3 : (pl->ops[o].tc ? 1 : 0));
+    if (engine) engine[o] = (pl->front_ok && o < 3) ? 2 : ((pl->ops[o].back || (pl->ops[o].tc && pl->ops[o].tcd.f16)) ? 3 : (pl->ops[o].tc ? 1 : 0));
     if (alg_flops) alg_flops[o] = double(pl->ops[o].alg_flops);
     if (exe_flops) exe_flops[o] = double(pl->ops[o].exe_flops);
   }

@@ -124,10 +124,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
-               : "memory");
-}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -138,17 +134,6 @@ template <int NC>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {      // NC columns, multiple of 8
 #pragma unroll
   for (int c = 0; c < NC; c += 8) tmem_ld8(taddr + c, v + c);
-}
-// two FP32 values -> FP16 pair (first value in the low half = the lower K index)
-__device__ __forceinline__ uint32_t fr_pack(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
-__device__ __forceinline__ void fr_split(float a, float b, uint32_t& hi, uint32_t& lo) {
-  hi = fr_pack(a, b);
-  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-  lo = fr_pack(a - hf.x, b - hf.y);
 }
 __device__ __forceinline__ void fr_tensor_load(void* dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile(

@@ -25,6 +25,8 @@
 // All hand-overs are mbarriers (full/free pairs); tcgen05.commit releases A stages, weight stages and
 // accumulators.  With two accumulator sets the epilogue of node i runs behind the MMAs of node i+1.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "layer.cuh"
 
 namespace hgsfa {
@@ -61,6 +63,10 @@ struct TcOpDev {
   int nd, nstx, nw, na;              // accumulator sets, receptive-field stages, weight-ring stages, A stages
   int head_floats, wchunk_floats;    // x_mean[d_pad4] | b[Npad16] | (m_i, m_j)[n_terms];  one weight chunk = hi[32][Npad16] | lo[32][Npad16]
   int tmem_cols;
+  int f16;                           // 1: 2-piece FP16 operands, tcgen05 kind::f16 (K = 16); 0: 3xTF32 (K = 8)
+  float scale;                       // accumulator scale of the epilogue (weights are stored times 1 / scale; 1 for TF32)
+  float prod_scale;                  // F16: operands of product terms are pre-scaled by this power of two (their weights by its
+                                     // inverse square) so that a product of two saturated inputs stays inside FP16's range; else 1
   float clip_lo, clip_hi;
   const Run* runs;
   const int* out_col;
@@ -159,32 +165,84 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
-// TF32 split of 8 values and store to the hi / lo column groups of an A stage
-__device__ __forceinline__ void tc_store8(uint32_t col_hi, const float (&v)[8]) {
-  // hi = v rounded to TF32 (nearest, ties away; two ALU ops), lo = v - hi exact in FP32.  The MMA ignores the
-  // low 13 bits of its FP32 containers (tools/tc_probe.cu mode 2), i.e. it truncates lo: |error| <= 2^-21 |v|.
-  // (hi = raw bits, lo = v - trunc(v) saves one op per term but doubles the error; measured 2.2e-4 x std
-  // against 1.1e-4 on U11L_64, profiles/README_r01.md)
-  uint32_t hi[8], lo[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    hi[j] = (__float_as_uint(v[j]) + 0x1000u) & 0xffffe000u;
-    lo[j] = __float_as_uint(v[j] - __uint_as_float(hi[j]));
-  }
-  tmem_st8(col_hi, hi);
-  tmem_st8(col_hi + TC_CK, lo);
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+// two FP32 values -> FP16 pair (first value in the low half = the lower K index)
+__device__ __forceinline__ uint32_t fr_pack(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void fr_split(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = fr_pack(a, b);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = fr_pack(a - hf.x, b - hf.y);
+}
+// instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t tc_idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
+      : "memory");
 }
 
-// values that are exactly representable in TF32 (uint8 pixels, identity terms): no split needed
-__device__ __forceinline__ void tc_store8_exact(uint32_t col_hi, const float (&v)[8]) {
-  uint32_t hi[8], lo[8];
+// Split of 8 values and store to the hi / lo column groups of an A stage.  `col`: tensor-memory address whose column field
+// counts TERMS from the start of the tensor memory (TF32: one column per term; F16: two terms per column, so the column
+// field is halved here -- the callers' arithmetic on 8-term groups is the same for both forms).
+template <bool F16>
+__device__ __forceinline__ void tc_store8(uint32_t col_hi, const float (&v)[8]) {
+  if constexpr (F16) {
+    // 2-piece FP16: hi = v rounded to FP16, lo = (v - hi) rounded to FP16: 22 significant bits like the TF32 pair, one
+    // 32-bit column per two terms (tools/tc_probe2.cu, profiles/README_r02.md)
+    const uint32_t t = (col_hi & 0xffff0000u) | ((col_hi & 0xffffu) >> 1);
+    uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    hi[j] = __float_as_uint(v[j]);
-    lo[j] = 0u;
+    for (int j = 0; j < 4; ++j) fr_split(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+    tmem_st4(t, hi);
+    tmem_st4(t + TC_CK / 2, lo);
+  } else {
+    // hi = v rounded to TF32 (nearest, ties away; two ALU ops), lo = v - hi exact in FP32.  The MMA ignores the
+    // low 13 bits of its FP32 containers (tools/tc_probe.cu mode 2), i.e. it truncates lo: |error| <= 2^-21 |v|.
+    // (hi = raw bits, lo = v - trunc(v) saves one op per term but doubles the error; measured 2.2e-4 x std
+    // against 1.1e-4 on U11L_64, profiles/README_r01.md)
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = (__float_as_uint(v[j]) + 0x1000u) & 0xffffe000u;
+      lo[j] = __float_as_uint(v[j] - __uint_as_float(hi[j]));
+    }
+    tmem_st8(col_hi, hi);
+    tmem_st8(col_hi + TC_CK, lo);
   }
-  tmem_st8(col_hi, hi);
-  tmem_st8(col_hi + TC_CK, lo);
+}
+
+// values that are exactly representable in one piece (uint8 pixels as identity terms; zero padding): no split needed
+template <bool F16>
+__device__ __forceinline__ void tc_store8_exact(uint32_t col_hi, const float (&v)[8]) {
+  if constexpr (F16) {
+    const uint32_t t = (col_hi & 0xffff0000u) | ((col_hi & 0xffffu) >> 1);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = fr_pack(v[2 * j], v[2 * j + 1]);
+      lo[j] = 0u;
+    }
+    tmem_st4(t, hi);
+    tmem_st4(t + TC_CK / 2, lo);
+  } else {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = __float_as_uint(v[j]);
+      lo[j] = 0u;
+    }
+    tmem_st8(col_hi, hi);
+    tmem_st8(col_hi + TC_CK, lo);
+  }
 }
 
 // one receptive-field value of this thread's window; xp already points at (row, window)
@@ -204,7 +262,7 @@ __device__ __forceinline__ float tc_row_value(const IN_T* xp, const float* mp, i
   if (MODE == 2) x = abspow(x, p);
   return x;
 }
-template <typename IN_T, int MODE>
+template <typename IN_T, int MODE, bool F16>
 __device__ __forceinline__ void tc_seg_rows(const IN_T* xp, const float* mp, int cnt, int ngroups, float p, uint32_t col) {
   // two groups (16 independent operand chains) per iteration while both are full: a warp issues in order, and
   // with one expansion warp per scheduler and CTA the instruction-level parallelism has to come from here
@@ -217,11 +275,11 @@ __device__ __forceinline__ void tc_seg_rows(const IN_T* xp, const float* mp, int
       v1[j] = tc_row_value<IN_T, MODE>(xp, mp, 8 + j, p);
     }
     if (sizeof(IN_T) == 1 && MODE == 0) {
-      tc_store8_exact(col, v0);
-      tc_store8_exact(col + 8, v1);
+      tc_store8_exact<F16>(col, v0);
+      tc_store8_exact<F16>(col + 8, v1);
     } else {
-      tc_store8(col, v0);
-      tc_store8(col + 8, v1);
+      tc_store8<F16>(col, v0);
+      tc_store8<F16>(col + 8, v1);
     }
   }
 #pragma unroll 1
@@ -234,8 +292,8 @@ __device__ __forceinline__ void tc_seg_rows(const IN_T* xp, const float* mp, int
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = tc_row_value<IN_T, MODE>(xp, mp, min(j, cnt - 1), p);
     }
-    if (sizeof(IN_T) == 1 && MODE == 0) tc_store8_exact(col, v);
-    else tc_store8(col, v);
+    if (sizeof(IN_T) == 1 && MODE == 0) tc_store8_exact<F16>(col, v);
+    else tc_store8<F16>(col, v);
   }
 }
 
@@ -253,7 +311,7 @@ __host__ __device__ constexpr int tri_col(int n, int idx) {
   while (idx >= len && len > 0) { idx -= len; --len; ++i; }
   return i + idx;
 }
-template <int N, int G>
+template <int N, int G, bool F16>
 __device__ __forceinline__ void tc_tri_groups(const float (&xc)[N], int g0, int g1, uint32_t col) {
   constexpr int T = N * (N + 1) / 2;
   if constexpr (8 * G < T) {
@@ -267,20 +325,23 @@ __device__ __forceinline__ void tc_tri_groups(const float (&xc)[N], int g0, int 
   }
       HG_TRI_TERM(0) HG_TRI_TERM(1) HG_TRI_TERM(2) HG_TRI_TERM(3) HG_TRI_TERM(4) HG_TRI_TERM(5) HG_TRI_TERM(6) HG_TRI_TERM(7)
 #undef HG_TRI_TERM
-      tc_store8(col + uint32_t(8 * (G - g0)), v);
+      tc_store8<F16>(col + uint32_t(8 * (G - g0)), v);
     }
-    tc_tri_groups<N, G + 1>(xc, g0, g1, col);
+    tc_tri_groups<N, G + 1, F16>(xc, g0, g1, col);
   }
 }
-template <typename IN_T, int N>
-__device__ __forceinline__ void tc_seg_tri(const IN_T* xr, const float* mr, int t0, int cnt, uint32_t col) {
+template <typename IN_T, int N, bool F16>
+__device__ __forceinline__ void tc_seg_tri(const IN_T* xr, const float* mr, int t0, int cnt, uint32_t col, float sc) {
   float xc[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) xc[i] = tc_ld<IN_T>(xr + i * TILE) - mr[i];
-  tc_tri_groups<N, 0>(xc, t0 >> 3, (t0 + cnt + 7) >> 3, col);
+  for (int i = 0; i < N; ++i) {
+    xc[i] = tc_ld<IN_T>(xr + i * TILE) - mr[i];
+    if constexpr (F16) xc[i] *= sc;          // products of saturated inputs must stay inside FP16's range
+  }
+  tc_tri_groups<N, 0, F16>(xc, t0 >> 3, (t0 + cnt + 7) >> 3, col);
 }
 
-template <typename IN_T>
+template <typename IN_T, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
     layer_tc_kernel(const TcOpDev op, const IN_T* __restrict__ xin, float* __restrict__ xout, int64_t ntiles) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -327,6 +388,8 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
   const uint32_t a_col0 = uint32_t(nd * op.twc * op.Npad16);          // A stages follow the accumulator sets
+  constexpr uint32_t A_STAGE = F16 ? TC_CK : 2 * TC_CK;               // columns of one A stage (hi | lo)
+  constexpr uint32_t A_LO = F16 ? TC_CK / 2 : TC_CK;                  // lo pieces follow the hi pieces
 
   if (warp == TC_PROD_WARP) {
     // ================================ producer ================================
@@ -374,9 +437,10 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
     // ================================ MMA issue ================================
     const bool leader = elect_one();
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
-    const uint32_t idesc = tc_idesc(op.Npad16);
+    const uint32_t idesc = F16 ? tc_idesc_f16(op.Npad16) : tc_idesc(op.Npad16);
+    // canonical K-major core matrices (8 rows x 16 bytes): a K step of one MMA (8 TF32 or 16 FP16 terms) spans two of them
     const uint32_t lbo = uint32_t(op.Npad16 / 8) * 128u, sbo = 128u;
-    const uint32_t lo_off = uint32_t(TC_CK * op.Npad16) * 4u;         // lo image follows the hi image
+    const uint32_t lo_off = uint32_t(TC_CK * op.Npad16) * (F16 ? 2u : 4u);   // lo image follows the hi image
     Ring rw(nw), ra(na), rd(nd);
     for (int node = node_begin; node < node_end; ++node, rd.next()) {
       const int set = rd.idx;
@@ -385,7 +449,8 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
         const int sw = rw.idx;
         mbar_wait_tc<HGSFA_TC_SLEEP_MMA>(&bars[TCB_WFULL + sw], rw.par);
         const uint32_t wbase = smem_u32(smem + op.sm_w0 + size_t(sw) * op.sm_wstage_bytes);
-        const int ksteps = (min(op.Kpad - c * TC_CK, TC_CK)) >> 3;
+        const int kterms = min(op.Kpad - c * TC_CK, TC_CK);
+        const int ksteps = F16 ? (kterms + 15) >> 4 : kterms >> 3;        // F16: an odd last 8-term group is zero-filled to 16
         for (int t = 0; t < vt; ++t, ra.next()) {
           if (c == 0) mbar_wait_tc<HGSFA_TC_SLEEP_MMA>(&bars[TCB_DFREE + set * TC_MAX_TW + t], dfree_par);
           const int sa = ra.idx;
@@ -393,13 +458,19 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
           tc_fence_after();
           if (leader) {
             const uint32_t d_t = tb + uint32_t((set * op.twc + t) * op.Npad16);
-            const uint32_t a_hi = tb + a_col0 + uint32_t(sa * 2 * TC_CK);
+            const uint32_t a_hi = tb + a_col0 + uint32_t(sa) * A_STAGE;
             for (int j = 0; j < ksteps; ++j) {
               const uint64_t bhi = tc_desc(wbase + uint32_t(2 * j) * lbo, lbo, sbo);
               const uint64_t blo = tc_desc(wbase + lo_off + uint32_t(2 * j) * lbo, lbo, sbo);
-              tc_mma(d_t, a_hi + 8 * j, bhi, idesc, (c | j) ? 1u : 0u);
-              tc_mma(d_t, a_hi + 8 * j, blo, idesc, 1u);
-              tc_mma(d_t, a_hi + TC_CK + 8 * j, bhi, idesc, 1u);
+              if constexpr (F16) {
+                tc_mma_f16(d_t, a_hi + 8 * j, bhi, idesc, (c | j) ? 1u : 0u);
+                tc_mma_f16(d_t, a_hi + 8 * j, blo, idesc, 1u);
+                tc_mma_f16(d_t, a_hi + A_LO + 8 * j, bhi, idesc, 1u);
+              } else {
+                tc_mma(d_t, a_hi + 8 * j, bhi, idesc, (c | j) ? 1u : 0u);
+                tc_mma(d_t, a_hi + 8 * j, blo, idesc, 1u);
+                tc_mma(d_t, a_hi + A_LO + 8 * j, bhi, idesc, 1u);
+              }
             }
             tc_commit(&bars[TCB_AFREE + sa]);
             if (c == n_chunks - 1) tc_commit(&bars[TCB_DFULL + set * TC_MAX_TW + t]);
@@ -426,7 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
         mbar_wait_tc<HGSFA_TC_SLEEP_EPI>(&bars[TCB_DFULL + set * TC_MAX_TW + t], par);
         tc_fence_after();
         float* out = xout + (size_t(tile0 + t) * op.out_dim + col0) * TILE + win;
-        const float clo = op.clip_lo, chi = op.clip_hi;
+        const float clo = op.clip_lo, chi = op.clip_hi, sc = op.scale;
         for (int n0 = 0; n0 < op.Npad16; n0 += 16, out += 16 * TILE) {
           uint32_t v[16];
           tmem_ld16(lane_base + uint32_t((set * op.twc + t) * op.Npad16 + n0), v);
@@ -441,10 +512,10 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + 4 * q);
-            y[4 * q + 0] = fminf(fmaxf(__uint_as_float(v[4 * q + 0]) + b4.x, clo), chi);
-            y[4 * q + 1] = fminf(fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, clo), chi);
-            y[4 * q + 2] = fminf(fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, clo), chi);
-            y[4 * q + 3] = fminf(fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, clo), chi);
+            y[4 * q + 0] = fminf(fmaxf(F16 ? fmaf(__uint_as_float(v[4 * q + 0]), sc, b4.x) : __uint_as_float(v[4 * q + 0]) + b4.x, clo), chi);
+            y[4 * q + 1] = fminf(fmaxf(F16 ? fmaf(__uint_as_float(v[4 * q + 1]), sc, b4.y) : __uint_as_float(v[4 * q + 1]) + b4.y, clo), chi);
+            y[4 * q + 2] = fminf(fmaxf(F16 ? fmaf(__uint_as_float(v[4 * q + 2]), sc, b4.z) : __uint_as_float(v[4 * q + 2]) + b4.z, clo), chi);
+            y[4 * q + 3] = fminf(fmaxf(F16 ? fmaf(__uint_as_float(v[4 * q + 3]), sc, b4.w) : __uint_as_float(v[4 * q + 3]) + b4.w, clo), chi);
           }
           if (nleft >= 16) {
 #pragma unroll
@@ -492,24 +563,26 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
           mbar_wait_tc(&bars[TCB_AFREE + sa], ra.par ^ 1u);
           tc_fence_after();
           const IN_T* xs = reinterpret_cast<const IN_T*>(stage + size_t(t) * op.sm_raw_bytes);
-          const uint32_t a_stage = lane_base + a_col0 + uint32_t(sa * 2 * TC_CK) - uint32_t(c * TC_CK);   // + k = hi column
+          // term-unit address of the stage's first term (see tc_store8): TF32 one column per term, F16 two terms per column
+          const uint32_t a_stage = F16 ? ((lane_base & 0xffff0000u) | (2u * ((lane_base & 0xffffu) + a_col0 + uint32_t(sa) * A_STAGE)))
+                                       : lane_base + a_col0 + uint32_t(sa) * A_STAGE;
           for (int sgi = sg0; sgi < sg1; ++sgi) {
             const Seg sg = segs[sgi];
             const int cnt = sg.kind, ngroups = (sg.k1 - sg.k0) >> 3;     // kind = number of real terms of the piece
-            const uint32_t col = a_stage + uint32_t(sg.k0);
+            const uint32_t col = a_stage + uint32_t(sg.k0 - c * TC_CK);
             if (sg.ibase >= 0 && (sg.op == OP_ID || sg.op == OP_ABSPOW)) {
               const IN_T* xp = xs + size_t(sg.ibase) * TILE + win;
               const float* mp = mean + sg.ibase;
-              if (sg.op == OP_ABSPOW) tc_seg_rows<IN_T, 2>(xp, mp, cnt, ngroups, sg.p, col);
-              else if (sg.nomean) tc_seg_rows<IN_T, 0>(xp, mp, cnt, ngroups, 0.f, col);
-              else tc_seg_rows<IN_T, 1>(xp, mp, cnt, ngroups, 0.f, col);
+              if (sg.op == OP_ABSPOW) tc_seg_rows<IN_T, 2, F16>(xp, mp, cnt, ngroups, sg.p, col);
+              else if (sg.nomean) tc_seg_rows<IN_T, 0, F16>(xp, mp, cnt, ngroups, 0.f, col);
+              else tc_seg_rows<IN_T, 1, F16>(xp, mp, cnt, ngroups, 0.f, col);
               continue;
             }
             if (sg.op == OP_TRI) {
               const IN_T* xr = xs + size_t(sg.ibase) * TILE + win;
               const float* mr = mean + sg.ibase;
               switch (int(sg.p)) {
-#define HG_TRI(N_) case N_: tc_seg_tri<IN_T, N_>(xr, mr, sg.nomean, cnt, col); break;
+#define HG_TRI(N_) case N_: tc_seg_tri<IN_T, N_, F16>(xr, mr, sg.nomean, cnt, col, op.prod_scale); break;
                 HG_TRI(3) HG_TRI(4) HG_TRI(5) HG_TRI(6) HG_TRI(7) HG_TRI(8) HG_TRI(9) HG_TRI(10) HG_TRI(11) HG_TRI(12)
                 HG_TRI(13) HG_TRI(14) HG_TRI(15) HG_TRI(16)
 #undef HG_TRI
@@ -530,7 +603,10 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
                   const int kk = min(8 * g + j, cnt - 1);
                   const int2 o = to[kk];
                   const float2 m = tm2[kk];
-                  v[j] = (tc_ld<IN_T>(xt + o.x) - m.x) * (tc_ld<IN_T>(xt + o.y) - m.y);
+                  if constexpr (F16)
+                    v[j] = ((tc_ld<IN_T>(xt + o.x) - m.x) * op.prod_scale) * ((tc_ld<IN_T>(xt + o.y) - m.y) * op.prod_scale);
+                  else
+                    v[j] = (tc_ld<IN_T>(xt + o.x) - m.x) * (tc_ld<IN_T>(xt + o.y) - m.y);
                 }
               } else {
 #pragma unroll
@@ -554,7 +630,16 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
                   v[j] = r;
                 }
               }
-              tc_store8(col + 8 * g, v);
+              tc_store8<F16>(col + 8 * g, v);
+            }
+          }
+          if constexpr (F16) {
+            // a K step of the FP16 MMA covers 16 terms: zero the second half of an odd last group (its weight rows are
+            // zero too, but stale tensor-memory bits could be NaN patterns)
+            const int kterms = min(op.Kpad - c * TC_CK, TC_CK);
+            if (kterms & 8) {
+              const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              tc_store8_exact<true>(a_stage + uint32_t(kterms), z);
             }
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

@@ -288,6 +288,28 @@ def test_plan_creation_order_does_not_matter(u11l96_flow, tiny_flow):
     small.close()
 
 
+def test_layer_kernel_fp16_pieces_opt_in(u11l_flow, monkeypatch):
+    """HGSFA_TC_F16=1: layer_tc_kernel takes 2-piece FP16 operands (tcgen05 kind::f16) for every op whose inputs are bounded
+    by the previous op's saturation -- layers 3-10 behind the fused front, layers 1-10 of the per-layer path (the first op
+    sees unbounded caller input and stays on 3xTF32).  Default: 3xTF32 pieces everywhere.  Both within TOL of the oracle."""
+    from pyfaceanalysis_b200 import GpuFlow, synthetic
+    x = synthetic.synthetic_patches(300, (64, 64), 33)
+    g0 = GpuFlow(u11l_flow)
+    monkeypatch.setenv("HGSFA_TC_F16", "1")
+    g1 = GpuFlow(u11l_flow)
+    monkeypatch.delenv("HGSFA_TC_F16")
+    errs = []
+    for g, want in ((g0, "tc"), (g1, "f16")):
+        errs.append(_check(g, u11l_flow, x, std=u11l_flow._train_output_std))
+        g.profile(True)
+        g.execute(x)
+        assert [s["engine"] for s in g.op_stats()] == ["front"] * 3 + [want] * 8
+        xf = x[:130].astype(np.float32)                                    # float input: per-layer ops only
+        _check(g, u11l_flow, xf, std=u11l_flow._train_output_std)
+        g.close()
+    print("U11L_64 max err/std: 3xTF32 layers %.3g, FP16-piece layers %.3g" % tuple(errs))
+
+
 def test_single_layer_fp16_kernel_opt_in(u11l_flow, monkeypatch):
     """HGSFA_BACK=1: the layers behind the fused front run on the single-layer FP16-split kernel (csrc/back_tc.cuh) --
     kept because it is the more accurate of the two tensor-core layer kernels, off by default because it is slower."""
