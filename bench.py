@@ -350,7 +350,7 @@ def run_detect(args, rank, world, local_rank, dev, barrier, dist):
         allr = pending.result()
         return allr, out[-1][1]
 
-    steps = max(n_lanes, min(args.steps, 6) // n_lanes * n_lanes)      # a multiple of the lanes
+    steps = max(n_lanes, min(max(args.steps, 6), 12) // n_lanes * n_lanes)      # 6..12 batches, a multiple of the lanes
     allr, tr = run(max(n_lanes, min(args.warmup, 2) * n_lanes))
     torch.cuda.synchronize(dev)
     barrier()
