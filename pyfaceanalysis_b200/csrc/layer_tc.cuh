@@ -53,6 +53,10 @@ constexpr int TC_MAX_TW = 8;
 #define HGSFA_TC_SLEEP_MMA 64
 #endif
 
+#ifndef HGSFA_TC_UNROLL16
+#define HGSFA_TC_UNROLL16 1   // unroll factor of the 16-term segment loop (2 measured: see profiles/README_r02.md item 13)
+#endif
+constexpr int TC_UNROLL16 = HGSFA_TC_UNROLL16;
 #ifndef HGSFA_TC_MINB
 #define HGSFA_TC_MINB 1     // resident CTAs per SM the register allocation is sized for
 #endif
@@ -266,7 +270,7 @@ template <typename IN_T, int MODE, bool F16>
 __device__ __forceinline__ void tc_seg_rows(const IN_T* xp, const float* mp, int cnt, int ngroups, float p, uint32_t col) {
   // two groups (16 independent operand chains) per iteration while both are full: a warp issues in order, and
   // with one expansion warp per scheduler and CTA the instruction-level parallelism has to come from here
-#pragma unroll 1
+#pragma unroll TC_UNROLL16
   for (; ngroups >= 2 && cnt >= 16; ngroups -= 2, cnt -= 16, xp += 16 * TILE, mp += 16, col += 16) {
     float v0[8], v1[8];
 #pragma unroll
