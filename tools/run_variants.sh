@@ -1,3 +1,5 @@
+# builder tool (record of the end-of-round-2 occupancy experiment, profiles/README_r02.md item 11): the variant libraries
+# are built first with tools/build_variant.py NAME flow.cu -D... into build/variants/ (not kept in the tree)
 set -x
 V=build/variants
 python tools/front_time.py 524288
