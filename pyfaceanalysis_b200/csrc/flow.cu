@@ -950,6 +950,14 @@ extern "C" int hgsfa_plan_flops(hgsfa_plan_t pl, int64_t n, int x_dtype, double*
   return 0;
 }
 
+#ifdef HGSFA_TC_TRACE
+extern "C" int hgsfa_debug_trace(unsigned long long* out, int n) {
+  HG_CUDA(cudaDeviceSynchronize());
+  HG_CUDA(cudaMemcpyFromSymbol(out, tc_trace, sizeof(unsigned long long) * size_t(n)));
+  return 0;
+}
+#endif
+
 extern "C" int hgsfa_plan_stats(hgsfa_plan_t pl, int64_t* launches, double* last_ms) {
   HG_CHECK(pl, "hgsfa_plan_stats: null plan");
   if (launches) *launches = pl->launches;

@@ -61,6 +61,21 @@ constexpr int TC_UNROLL16 = HGSFA_TC_UNROLL16;
 #define HGSFA_TC_MINB 1     // resident CTAs per SM the register allocation is sized for
 #endif
 
+#ifdef HGSFA_TC_TRACE
+// development: time stamps of expansion warp 0 of one CTA of the op with HGSFA_TC_TRACE nodes (tools/tc_trace.py)
+__device__ unsigned long long tc_trace[16384];
+#define TC_T(slot)                                                                                            \
+  do {                                                                                                        \
+    if (tracing && tcnt < 16380) tc_trace[tcnt++] = ((unsigned long long)clock64() << 8) | (unsigned long long)(slot); \
+  } while (0)
+#define TC_TRACE_PARAM , bool tracing, int& tcnt
+#define TC_TRACE_ARG , tracing, tcnt
+#else
+#define TC_T(slot) do { } while (0)
+#define TC_TRACE_PARAM
+#define TC_TRACE_ARG
+#endif
+
 struct TcOpDev {
   int n_nodes, d_in, in_dim, out_dim, shared, twc, npc, n_runs;
   int K, Kpad, Npad16, n_chunks, n_terms, n_segs;
@@ -267,17 +282,23 @@ __device__ __forceinline__ float tc_row_value(const IN_T* xp, const float* mp, i
   return x;
 }
 template <typename IN_T, int MODE, bool F16>
-__device__ __forceinline__ void tc_seg_rows(const IN_T* xp, const float* mp, int cnt, int ngroups, float p, uint32_t col) {
+__device__ __forceinline__ void tc_seg_rows(const IN_T* xp, const float* mp, int cnt, int ngroups, float p, uint32_t col TC_TRACE_PARAM) {
   // two groups (16 independent operand chains) per iteration while both are full: a warp issues in order, and
   // with one expansion warp per scheduler and CTA the instruction-level parallelism has to come from here
 #pragma unroll TC_UNROLL16
   for (; ngroups >= 2 && cnt >= 16; ngroups -= 2, cnt -= 16, xp += 16 * TILE, mp += 16, col += 16) {
     float v0[8], v1[8];
+    TC_T(8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       v0[j] = tc_row_value<IN_T, MODE>(xp, mp, j, p);
       v1[j] = tc_row_value<IN_T, MODE>(xp, mp, 8 + j, p);
     }
+#ifdef HGSFA_TC_TRACE
+    asm volatile("" ::"f"(v0[0]), "f"(v0[1]), "f"(v0[2]), "f"(v0[3]), "f"(v0[4]), "f"(v0[5]), "f"(v0[6]), "f"(v0[7]), "f"(v1[0]),
+                 "f"(v1[1]), "f"(v1[2]), "f"(v1[3]), "f"(v1[4]), "f"(v1[5]), "f"(v1[6]), "f"(v1[7]));
+#endif
+    TC_T(9);
     if (sizeof(IN_T) == 1 && MODE == 0) {
       tc_store8_exact<F16>(col, v0);
       tc_store8_exact<F16>(col + 8, v1);
@@ -285,6 +306,7 @@ __device__ __forceinline__ void tc_seg_rows(const IN_T* xp, const float* mp, int
       tc_store8<F16>(col, v0);
       tc_store8<F16>(col + 8, v1);
     }
+    TC_T(10);
   }
 #pragma unroll 1
   for (; ngroups > 0; --ngroups, cnt -= 8, xp += 8 * TILE, mp += 8, col += 8) {
@@ -542,11 +564,17 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
         epilogue(node, rd.idx, rd.par, bias_buf + slot * op.Npad16);
     } else {
     Ring rx(nstx), ra(na), rd(nd);
+#ifdef HGSFA_TC_TRACE
+    const bool tracing = op.n_nodes == HGSFA_TC_TRACE && blockIdx.x == 9 && blockIdx.y == 0 && warp == 0 && lane == 0;
+    int tcnt = 1;
+#endif
     int prev_set = 0, slot = 0;
     uint32_t prev_par = 0u;
     for (int node = node_begin; node < node_end; ++node, rx.next(), rd.next(), slot = (slot + 1) & 7) {
       const int sx = rx.idx;
+      TC_T(0);
       mbar_wait_tc(&bars[TCB_XFULL + sx], rx.par);
+      TC_T(1);
       const uint8_t* stage = smem + op.sm_x0 + size_t(sx) * op.sm_xstage_bytes;
       const float* head = reinterpret_cast<const float*>(stage + size_t(op.twc) * op.sm_raw_bytes);
       const float* mean = head;
@@ -564,8 +592,10 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
         const int sg0 = chunk_seg[c], sg1 = chunk_seg[c + 1];
         for (int t = 0; t < vt; ++t, ra.next()) {
           const int sa = ra.idx;
+          TC_T(2);
           mbar_wait_tc(&bars[TCB_AFREE + sa], ra.par ^ 1u);
           tc_fence_after();
+          TC_T(3);
           const IN_T* xs = reinterpret_cast<const IN_T*>(stage + size_t(t) * op.sm_raw_bytes);
           // term-unit address of the stage's first term (see tc_store8): TF32 one column per term, F16 two terms per column
           const uint32_t a_stage = F16 ? ((lane_base & 0xffff0000u) | (2u * ((lane_base & 0xffffu) + a_col0 + uint32_t(sa) * A_STAGE)))
@@ -577,9 +607,9 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
             if (sg.ibase >= 0 && (sg.op == OP_ID || sg.op == OP_ABSPOW)) {
               const IN_T* xp = xs + size_t(sg.ibase) * TILE + win;
               const float* mp = mean + sg.ibase;
-              if (sg.op == OP_ABSPOW) tc_seg_rows<IN_T, 2, F16>(xp, mp, cnt, ngroups, sg.p, col);
-              else if (sg.nomean) tc_seg_rows<IN_T, 0, F16>(xp, mp, cnt, ngroups, 0.f, col);
-              else tc_seg_rows<IN_T, 1, F16>(xp, mp, cnt, ngroups, 0.f, col);
+              if (sg.op == OP_ABSPOW) tc_seg_rows<IN_T, 2, F16>(xp, mp, cnt, ngroups, sg.p, col TC_TRACE_ARG);
+              else if (sg.nomean) tc_seg_rows<IN_T, 0, F16>(xp, mp, cnt, ngroups, 0.f, col TC_TRACE_ARG);
+              else tc_seg_rows<IN_T, 1, F16>(xp, mp, cnt, ngroups, 0.f, col TC_TRACE_ARG);
               continue;
             }
             if (sg.op == OP_TRI) {
@@ -646,14 +676,18 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
               tc_store8_exact<true>(a_stage + uint32_t(kterms), z);
             }
           }
+          TC_T(4);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
+          TC_T(5);
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[TCB_AFULL + sa]);
+          TC_T(6);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[TCB_XFREE + sx]);     // receptive field consumed
+      TC_T(7);
       if (!TC_EPI) {
         if (nd == 2) {
           if (node > node_begin) epilogue(node - 1, prev_set, prev_par, bias_buf + (warp * 2 + prev_set) * op.Npad16);
@@ -666,6 +700,9 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
     }
     if (!TC_EPI && nd == 2 && node_end > node_begin)
       epilogue(node_end - 1, prev_set, prev_par, bias_buf + (warp * 2 + prev_set) * op.Npad16);
+#ifdef HGSFA_TC_TRACE
+    if (tracing) tc_trace[0] = (unsigned long long)tcnt;
+#endif
     }
   }
 
