@@ -15,7 +15,7 @@ uniform integers 0..255, seed 12345600 (FaceDetectUpdated.py:146).  One step = o
           host->device copy of the windows and device->host copy of the (N, 60) float64 features are
           inside the timed region
   roofline : dominant kernel of the step (DESIGN.md section 6): hgsfa::front_kernel (layers 0-2 fused, tcgen05 kind::f16,
-          2-piece FP16 split: ceiling = measured bf16 peak / 3), hgsfa::layer_tc_kernel (tcgen05 3xTF32: bf16 peak / 6)
+          2-piece FP16 split: ceiling = measured bf16 peak / 3), hgsfa::layer_tc_kernel (FP16 pieces: bf16 peak / 3; 3xTF32: / 6)
           or hgsfa::layer_kernel (packed FP32 FMA: measured FFMA2 peak); achieved = algorithmic flops of that kernel's
           ops / its CUDA-event time inside the timed steps; every kernel of the step is listed under "kernels"
   detect : BASELINE configs[2] on the same clock -- 64 synthetic 1920x1080 images per GPU, smallest_face 0.05,
@@ -104,7 +104,8 @@ def _roofline(op_stats, steps, n, fl, kernel_ms_last, peaks, fp32_peak, fp32_src
     ceilings = {
         "front": ("hgsfa::front_kernel (layers 0-2 fused, lane-resident; tcgen05 kind::f16)", "tensor", bf16 / 3.0,
                   bf16_txt + " / 3 (2-piece FP16 split = 3 MMAs per algorithmic block)"),
-        "f16": ("hgsfa::back_kernel (one layer per launch, lane-resident; tcgen05 kind::f16)", "tensor", bf16 / 3.0,
+        "f16": ("hgsfa::layer_tc_kernel<F16> (one layer per launch; tcgen05 kind::f16 on 2-piece FP16 operands; hgsfa::back_kernel with "
+                "HGSFA_BACK=1)", "tensor", bf16 / 3.0,
                 bf16_txt + " / 3 (2-piece FP16 split = 3 MMAs per algorithmic block)"),
         "tc": ("hgsfa::layer_tc_kernel (tcgen05 kind::tf32)", "tensor", bf16 / 6.0,
                bf16_txt + " / 6 (TF32 = bf16 / 2; 3xTF32 split = 3 MMAs per algorithmic block)"),
@@ -603,7 +604,7 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16x2 split (fused front) / 3xtf32 (layer ops), f32 accumulation; f32 FFMA with HGSFA_ENGINE=ffma", "data": "synthetic",
+            "vs_baseline": None, "dtype": "2-piece f16 split (fused front and bounded layer ops) / 3xtf32 (unbounded inputs, HGSFA_TC_F16=0), f32 accumulation; f32 FFMA with HGSFA_ENGINE=ffma", "data": "synthetic",
             "config": {"workload": "configs[1]: U11L_64 (FaceCentering2-shaped synthetic HiGSFA flow) forward, "
                                    "%d windows x 4096 uint8 per GPU per step" % n,
                        "windows_per_gpu": n, "window_dim": g.input_dim, "features": F, "flow": FLOW_SPEC,

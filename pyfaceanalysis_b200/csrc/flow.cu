@@ -475,6 +475,11 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
         std::vector<Seg> tsegs;
         std::vector<int> knew(dp.K, 0);          // term k -> A column
         int cursor = 0;
+        int ck = TC_CK;                          // terms per chunk (TC_CK16 for the FP16 form, decided below)
+        const char* seg_error = nullptr;
+        auto build_segs = [&]() {
+        tsegs.clear();
+        cursor = 0;
         auto push = [&](Seg sgm) {               // sgm.k0 / k1: ORIGINAL term range
           int real = sgm.k1 - sgm.k0, tk = sgm.k0, ib = sgm.ibase;
           for (int k = sgm.k0; k < sgm.k1; ++k) knew[k] = cursor + (k - sgm.k0);
@@ -483,7 +488,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
           while (pos < end) {
             Seg piece = sgm;
             piece.k0 = pos;
-            piece.k1 = std::min(end, (pos / TC_CK + 1) * TC_CK);
+            piece.k1 = std::min(end, (pos / ck + 1) * ck);
             const int len = piece.k1 - piece.k0;
             piece.kind = std::min(real, len);
             piece.ibase = ib;
@@ -499,7 +504,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
         };
         for (int sgi = 0; sgi < dp.n_seg; ++sgi) {
           Seg sgm = segs[sgi];
-          if (sgm.kind != 0) return plan_fail(pl, "op %lld: tensor-core ops take receptive-field operands only", (long long)o);
+          if (sgm.kind != 0) { seg_error = "tensor-core ops take receptive-field operands only"; return; }
           if (sgm.op == OP_ID_POW) {
             const int half = (sgm.k1 - sgm.k0) / 2;
             Seg a = sgm, b = sgm;
@@ -524,24 +529,15 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
             push(sgm);
           }
         }
-        t.Kpad = cursor;
-        t.n_chunks = (t.Kpad + TC_CK - 1) / TC_CK;
-        std::vector<int32_t> chunk_seg(t.n_chunks + 1, 0);
-        {
-          size_t sgi = 0;
-          for (int c = 0; c < t.n_chunks; ++c) {
-            chunk_seg[c] = (int32_t)sgi;
-            while (sgi < tsegs.size() && tsegs[sgi].k0 < (c + 1) * TC_CK) ++sgi;
-          }
-          chunk_seg[t.n_chunks] = (int32_t)tsegs.size();
-        }
-        t.n_segs = (int)tsegs.size();
-        // ---- FP16 pieces instead of TF32 pieces (layer_tc.cuh, F16 = true; opt-in, HGSFA_TC_F16=1) where every operand
+        };
+        build_segs();
+        if (seg_error) return plan_fail(pl, "op %lld: %s", (long long)o, seg_error);
+        // ---- FP16 pieces instead of TF32 pieces (layer_tc.cuh, F16 = true; HGSFA_TC_F16=0 turns it off) where every operand
         // provably fits FP16's range: float inputs bounded by the previous op's saturation, term kinds with a known bound,
-        // operands of products pre-scaled.  Per unit of K the kind::f16 MMA holds the tensor pipe 3-4x shorter at N = 48-64,
-        // a weight chunk is half the bytes and the accuracy is the same (22 significant bits per operand) -- but measured on
-        // layers 3-10 of U11L_64 it is no faster (12.9 vs 12.7 ms per 1 Mi windows, profiles/README_r02.md item 13): neither
-        // the tensor pipe nor the weight stream is what holds these layers, so 3xTF32 (no range conditions) stays the default.
+        // operands of products pre-scaled.  Two terms share a tensor-memory column, so a chunk holds 64 terms in the columns
+        // and weight bytes the TF32 form needs for 32: half the hand-overs between the expansion warps and the MMA warp,
+        // which cost ~700 cycles each against ~1 200 for 32 terms of arithmetic (profiles/README_r02.md items 13-14).
+        // Layers 3-10 of U11L_64: 10.8 instead of 12.4 ms per 1 Mi windows; accuracy as 3xTF32 (22 significant bits).
         t.f16 = 0;
         t.scale = 1.0f;
         t.prod_scale = 1.0f;
@@ -549,7 +545,8 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
         std::vector<uint8_t> is_prod(dp.K, 0);
         {
           const char* env = getenv("HGSFA_TC_F16");
-          bool ok = env && env[0] == '1' && o > 0;
+          const char* env_back = getenv("HGSFA_BACK");                     // the single-layer kernel of back_tc.cuh takes these ops
+          bool ok = !(env && env[0] == '0') && !(env_back && env_back[0] == '1') && o > 0;
           double bound_c = 0.0;
           if (ok) {
             const OpDev& prev = pl->ops[o - 1].dev;
@@ -593,12 +590,23 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
             t.scale = (float)std::ldexp(1.0, -tpow);
             t.prod_scale = (float)std::ldexp(1.0, -prod_shift);
             f16_wmul = std::ldexp(1.0, tpow);
-            t.wchunk_floats = TC_CK * t.Npad16;                                // two FP16 images = half the bytes
-            const int cols16 = t.nd * t.twc * t.Npad16 + t.na * TC_CK;         // an A stage is TC_CK columns (two terms each)
-            t.tmem_cols = 32;
-            while (t.tmem_cols < cols16) t.tmem_cols *= 2;
+            // chunks of 2 x TC_CK terms: the same tensor-memory columns and weight-chunk bytes as the TF32 form
+            ck = TC_CK16;
+            build_segs();
           }
         }
+        t.Kpad = cursor;
+        t.n_chunks = (t.Kpad + ck - 1) / ck;
+        std::vector<int32_t> chunk_seg(t.n_chunks + 1, 0);
+        {
+          size_t sgi = 0;
+          for (int c = 0; c < t.n_chunks; ++c) {
+            chunk_seg[c] = (int32_t)sgi;
+            while (sgi < tsegs.size() && tsegs[sgi].k0 < (c + 1) * ck) ++sgi;
+          }
+          chunk_seg[t.n_chunks] = (int32_t)tsegs.size();
+        }
+        t.n_segs = (int)tsegs.size();
         // head = x_mean | bias;  weight chunks = TF32 hi image | lo image, canonical K-major core matrices
         const size_t head_bytes = size_t(n_w) * t.head_floats * 4;
         const size_t wimg_bytes = size_t(n_w) * t.n_chunks * t.wchunk_floats * 4;
@@ -617,7 +625,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
             head[size_t(w) * t.head_floats + d_pad + t.Npad16 + 2 * k + 1] = pw[terms[k].j];
           }
           for (int k = 0; k < dp.K; ++k) {
-            const int c = knew[k] / TC_CK, kk = knew[k] % TC_CK;
+            const int c = knew[k] / ck, kk = knew[k] % ck;
             float* img = wimg + (size_t(w) * t.n_chunks + c) * t.wchunk_floats;
             for (int n = 0; n < std::min(dp.Npad, t.Npad16); ++n) {
               const float wv = pw[dp.w_off + size_t(k) * dp.Npad + n];
@@ -628,7 +636,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
                 const double ws = double(wv) * f16_wmul * (is_prod[k] ? f16_prod_w : 1.0);
                 const __half h = __float2half_rn(float(ws));
                 hi16[off] = h;
-                hi16[size_t(TC_CK) * t.Npad16 + off] = __float2half_rn(float(ws - double(__half2float(h))));
+                hi16[size_t(TC_CK16) * t.Npad16 + off] = __float2half_rn(float(ws - double(__half2float(h))));
                 continue;
               }
               const float hi = tf32_rn(wv);
@@ -662,7 +670,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
           // opt-in (HGSFA_BACK=1): measured on U11L_64 it is correct and slightly more accurate than the 3xTF32 kernel but
           // 15 % slower with 8 expansion warps per SM (14.5 vs 12.5 ms for ops 3-10, profiles/README_r02.md)
           const char* env = getenv("HGSFA_BACK");
-          bool ok = env && env[0] == '1' && o > 0 && t.Npad16 <= 64 && t.n_chunks <= 64;
+          bool ok = env && env[0] == '1' && !t.f16 && o > 0 && t.Npad16 <= 64 && t.n_chunks <= 64;
           float bound_in = 0.f;
           if (ok) {
             const OpDev& prev = pl->ops[o - 1].dev;

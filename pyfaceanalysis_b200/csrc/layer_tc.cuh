@@ -34,7 +34,12 @@ namespace hgsfa {
 #ifndef HGSFA_TC_CK
 #define HGSFA_TC_CK 32
 #endif
-constexpr int TC_CK = HGSFA_TC_CK;   // terms per chunk (A stage = TC_CK hi + TC_CK lo columns)
+constexpr int TC_CK = HGSFA_TC_CK;   // terms per chunk of the TF32 form (A stage = TC_CK hi + TC_CK lo columns)
+// The FP16 form packs two terms per column: a chunk of 2 x TC_CK terms has the SAME footprint -- TC_CK hi + TC_CK lo columns,
+// a weight chunk of the same bytes -- and half the hand-overs per term (a hand-over costs ~700 cycles, a 32-term chunk of
+// arithmetic ~1 200: profiles/README_r02.md item 14).
+constexpr int TC_CK16 = 2 * TC_CK;
+__host__ __device__ constexpr int tc_chunk_terms(bool f16) { return f16 ? TC_CK16 : TC_CK; }
 #ifndef HGSFA_TC_EPI
 #define HGSFA_TC_EPI 1
 #endif
@@ -222,7 +227,7 @@ __device__ __forceinline__ void tc_store8(uint32_t col_hi, const float (&v)[8]) 
 #pragma unroll
     for (int j = 0; j < 4; ++j) fr_split(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
     tmem_st4(t, hi);
-    tmem_st4(t + TC_CK / 2, lo);
+    tmem_st4(t + TC_CK16 / 2, lo);
   } else {
     // hi = v rounded to TF32 (nearest, ties away; two ALU ops), lo = v - hi exact in FP32.  The MMA ignores the
     // low 13 bits of its FP32 containers (tools/tc_probe.cu mode 2), i.e. it truncates lo: |error| <= 2^-21 |v|.
@@ -251,7 +256,7 @@ __device__ __forceinline__ void tc_store8_exact(uint32_t col_hi, const float (&v
       lo[j] = 0u;
     }
     tmem_st4(t, hi);
-    tmem_st4(t + TC_CK / 2, lo);
+    tmem_st4(t + TC_CK16 / 2, lo);
   } else {
     uint32_t hi[8], lo[8];
 #pragma unroll
@@ -414,8 +419,9 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
   const uint32_t a_col0 = uint32_t(nd * op.twc * op.Npad16);          // A stages follow the accumulator sets
-  constexpr uint32_t A_STAGE = F16 ? TC_CK : 2 * TC_CK;               // columns of one A stage (hi | lo)
-  constexpr uint32_t A_LO = F16 ? TC_CK / 2 : TC_CK;                  // lo pieces follow the hi pieces
+  constexpr int CK = tc_chunk_terms(F16);                              // terms per chunk
+  constexpr uint32_t A_STAGE = 2 * TC_CK;                              // columns of one A stage (hi | lo), both forms
+  constexpr uint32_t A_LO = TC_CK;                                     // lo pieces follow the hi pieces
 
   if (warp == TC_PROD_WARP) {
     // ================================ producer ================================
@@ -466,7 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
     const uint32_t idesc = F16 ? tc_idesc_f16(op.Npad16) : tc_idesc(op.Npad16);
     // canonical K-major core matrices (8 rows x 16 bytes): a K step of one MMA (8 TF32 or 16 FP16 terms) spans two of them
     const uint32_t lbo = uint32_t(op.Npad16 / 8) * 128u, sbo = 128u;
-    const uint32_t lo_off = uint32_t(TC_CK * op.Npad16) * (F16 ? 2u : 4u);   // lo image follows the hi image
+    const uint32_t lo_off = uint32_t(TC_CK * op.Npad16) * 4u;        // lo image follows the hi image (CK x Npad16 elements)
     Ring rw(nw), ra(na), rd(nd);
     for (int node = node_begin; node < node_end; ++node, rd.next()) {
       const int set = rd.idx;
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
         const int sw = rw.idx;
         mbar_wait_tc<HGSFA_TC_SLEEP_MMA>(&bars[TCB_WFULL + sw], rw.par);
         const uint32_t wbase = smem_u32(smem + op.sm_w0 + size_t(sw) * op.sm_wstage_bytes);
-        const int kterms = min(op.Kpad - c * TC_CK, TC_CK);
+        const int kterms = min(op.Kpad - c * CK, CK);
         const int ksteps = F16 ? (kterms + 15) >> 4 : kterms >> 3;        // F16: an odd last 8-term group is zero-filled to 16
         for (int t = 0; t < vt; ++t, ra.next()) {
           if (c == 0) mbar_wait_tc<HGSFA_TC_SLEEP_MMA>(&bars[TCB_DFREE + set * TC_MAX_TW + t], dfree_par);
@@ -603,7 +609,7 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
           for (int sgi = sg0; sgi < sg1; ++sgi) {
             const Seg sg = segs[sgi];
             const int cnt = sg.kind, ngroups = (sg.k1 - sg.k0) >> 3;     // kind = number of real terms of the piece
-            const uint32_t col = a_stage + uint32_t(sg.k0 - c * TC_CK);
+            const uint32_t col = a_stage + uint32_t(sg.k0 - c * CK);
             if (sg.ibase >= 0 && (sg.op == OP_ID || sg.op == OP_ABSPOW)) {
               const IN_T* xp = xs + size_t(sg.ibase) * TILE + win;
               const float* mp = mean + sg.ibase;
@@ -670,7 +676,7 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
           if constexpr (F16) {
             // a K step of the FP16 MMA covers 16 terms: zero the second half of an odd last group (its weight rows are
             // zero too, but stale tensor-memory bits could be NaN patterns)
-            const int kterms = min(op.Kpad - c * TC_CK, TC_CK);
+            const int kterms = min(op.Kpad - c * CK, CK);
             if (kterms & 8) {
               const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               tc_store8_exact<true>(a_stage + uint32_t(kterms), z);

@@ -73,7 +73,7 @@ def test_u11l_both_engines(u11l_flow, engine, monkeypatch):
     st = g.op_stats()
     assert len(st) == 11
     if engine == "tc":      # uint8 windows: layers 0-2 run as one fused launch whose time is booked on op 0
-        assert [s["engine"] for s in st] == ["front"] * 3 + ["tc"] * 8
+        assert [s["engine"] for s in st] == ["front"] * 3 + ["f16"] * 8      # layers 3-10: layer_tc_kernel on FP16 pieces
         assert st[0]["ms"] > 0 and st[1]["ms"] == 0 and st[2]["ms"] == 0 and all(s["ms"] > 0 for s in st[3:])
     else:
         assert all(s["engine"] == engine and s["ms"] > 0 for s in st)
@@ -118,8 +118,9 @@ def test_fused_front_matches_per_layer_path(u11l_flow, monkeypatch):
             wide[:, :4096] = xt
             y_w = fused.execute_torch(wide[:, :4096]).cpu().numpy().astype(np.float64)
             assert np.array_equal(y_w, y_f)
-    assert [s["engine"] for s in fused.op_stats()][:4] == ["front", "front", "front", "tc"]
-    assert [s["engine"] for s in plain.op_stats()][:3] == ["tc", "tc", "tc"] and plain.op_stats()[1]["ms"] > 0
+    assert [s["engine"] for s in fused.op_stats()][:4] == ["front", "front", "front", "f16"]
+    # per-layer path: the first op (unbounded caller input) on 3xTF32, bounded ones on FP16 pieces
+    assert [s["engine"] for s in plain.op_stats()][:3] == ["tc", "f16", "f16"] and plain.op_stats()[1]["ms"] > 0
     # host entry point (pieces through the staging buffers) and float input (per-layer path, exact same values as `plain`)
     xh = rng.integers(0, 256, (70000, 4096), dtype=np.uint8)
     y_f, y_p = fused.execute(xh, out_dtype=np.float32), plain.execute(xh, out_dtype=np.float32)
@@ -288,16 +289,17 @@ def test_plan_creation_order_does_not_matter(u11l96_flow, tiny_flow):
     small.close()
 
 
-def test_layer_kernel_fp16_pieces_opt_in(u11l_flow, monkeypatch):
-    """HGSFA_TC_F16=1: layer_tc_kernel takes 2-piece FP16 operands (tcgen05 kind::f16) for every op whose inputs are bounded
-    by the previous op's saturation -- layers 3-10 behind the fused front, layers 1-10 of the per-layer path (the first op
-    sees unbounded caller input and stays on 3xTF32).  Default: 3xTF32 pieces everywhere.  Both within TOL of the oracle."""
+def test_layer_kernel_tf32_pieces_opt_out(u11l_flow, monkeypatch):
+    """Default: layer_tc_kernel takes 2-piece FP16 operands (tcgen05 kind::f16, 64-term chunks) for every op whose inputs
+    are bounded by the previous op's saturation -- layers 3-10 behind the fused front, layers 1-10 of the per-layer path
+    (the first op sees unbounded caller input and stays on 3xTF32).  HGSFA_TC_F16=0: 3xTF32 pieces everywhere (round 1's
+    arithmetic).  Both within TOL of the float64 oracle."""
     from pyfaceanalysis_b200 import GpuFlow, synthetic
     x = synthetic.synthetic_patches(300, (64, 64), 33)
+    monkeypatch.setenv("HGSFA_TC_F16", "0")
     g0 = GpuFlow(u11l_flow)
-    monkeypatch.setenv("HGSFA_TC_F16", "1")
-    g1 = GpuFlow(u11l_flow)
     monkeypatch.delenv("HGSFA_TC_F16")
+    g1 = GpuFlow(u11l_flow)
     errs = []
     for g, want in ((g0, "tc"), (g1, "f16")):
         errs.append(_check(g, u11l_flow, x, std=u11l_flow._train_output_std))
