@@ -28,8 +28,10 @@
 //   warp 18          producer: pixel boxes (3-D tensor map over row-major windows, or bulk copies of window-minor
 //                    tiles) and weight chunks (cp.async.bulk) through mbarrier rings
 // Item order per subtree s (software-pipelined so that no item depends on the one issued just before it):
-//   L0a(s) L0b(s) L2(s-1) L0c(s) L0d(s) L1ab(s) STORE(s-1) L1cd(s)
-// Tensor-memory columns per group: 4 x 16 (level-0 accumulators) + 2 x 32 (level 1) + 32 (level 2) + 3 x 32 (A ring).
+//   L0ab(s) L2(s-1) L1ab(s) L0cd(s) STORE(s-1) L1cd(s)
+// An A stage holds TWO 32-term chunks (two layer-0 nodes, or two chunks of a join) per hand-over; a pair of layer-0 nodes is
+// drained by its join before the next pair is issued, so two accumulator slots serve the four nodes.
+// Tensor-memory columns per group: 2 x 16 (level-0 accumulators) + 2 x 32 (level 1) + 32 (level 2) + 2 x 64 (A ring).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -40,7 +42,8 @@
 namespace hgsfa {
 
 constexpr int FR_NW = 6;                 // weight-ring stages
-constexpr int FR_NA = 3;                 // A-ring stages per group (32 columns each: 16 hi + 16 lo)
+constexpr int FR_NA = 2;                 // A-ring stages per group: 64 columns = TWO 32-term chunks (hi: 16 + 16 columns, then lo:
+                                         // 16 + 16) per hand-over -- a hand-over costs ~700 cycles (profiles/README_r02.md item 14)
 constexpr int FR_NX = 2;                 // pixel-box stages per group
 constexpr int FR_WSTAGE = FR_HEAD + 32 * 128;
 constexpr int FR_XSTAGE = 16 * 8 * TILE;  // 16 x 8 pixel box of 128 windows
@@ -58,7 +61,9 @@ constexpr int FR_THREADS = (FR_EXP_WARPS + 3) * 32;
 constexpr bool FR_LAZY_PUBLISH = HGSFA_FR_LAZY_PUBLISH != 0;
 constexpr int FR_SLEEP_MMA = HGSFA_FR_SLEEP_MMA, FR_SLEEP_PROD = HGSFA_FR_SLEEP_PROD;   // ns between barrier tries of the service warps
 constexpr int FR_GCOLS = 256;            // tensor-memory columns per group
-constexpr int FR_COL_L0 = 0, FR_COL_L1 = 64, FR_COL_L2 = 128, FR_COL_A = 160;
+// accumulators: layer 0 two slots of 16 columns (a pair of nodes is drained by its join before the next pair is issued),
+// layer 1 two of 32, layer 2 one of 32; then the A ring
+constexpr int FR_COL_L0 = 0, FR_COL_L1 = 32, FR_COL_L2 = 96, FR_COL_A = 128, FR_ASTAGE = 64, FR_ALO = 32;
 // barriers: WFULL[6] WFREE[6] then per group AFULL[3] AFREE[3] DFULL[7] XFULL[2] XFREE[2]
 enum { FRB_WFULL = 0, FRB_WFREE = FR_NW, FRB_G = 2 * FR_NW, FRB_AFULL = 0, FRB_AFREE = FR_NA, FRB_DFULL = 2 * FR_NA,
        FRB_XFULL = 2 * FR_NA + 7, FRB_XFREE = 2 * FR_NA + 7 + FR_NX, FRB_GSTRIDE = 2 * FR_NA + 7 + 2 * FR_NX,
@@ -167,6 +172,7 @@ struct FrJoin {
       }
     }
     constexpr int NCH = NP / 8;
+    uint32_t stage = 0;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       uint32_t hi[8], lo[8];
@@ -187,10 +193,11 @@ struct FrJoin {
         fr_split(v[0], v[1], hi[q], lo[q]);
         fr_split(v[2], v[3], hi[q + 1], lo[q + 1]);
       }
-      const uint32_t col = publish.acquire() + uint32_t(8 * half);
+      if ((c & 1) == 0) stage = publish.acquire();          // a stage holds two chunks: hi columns 16 (c & 1) + ..., lo after 32
+      const uint32_t col = stage + uint32_t(16 * (c & 1) + 8 * half);
       tmem_st8(col, hi);
-      tmem_st8(col + 16, lo);
-      publish.release();
+      tmem_st8(col + FR_ALO, lo);
+      if ((c & 1) == 1 || c == NCH - 1) publish.release();
     }
   }
 };
@@ -263,21 +270,22 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
       const int cb0 = FR_HEAD + fd.nn0 * 128, cb1 = FR_HEAD + fd.nn1 * 128, cb2 = FR_HEAD + fd.nn2 * 128;
       const int off_l1 = 4 * cb0, off_l2 = off_l1 + 2 * NCH1 * cb1;
       load_pixels(s_begin / 2);
-      // every role walks the same 8 item slots per subtree iteration, each body instantiated once (code size: the
-      // kernel must stay inside the instruction cache):  0 L0a  1 L0b  2 L2(s-1)  3 L0c  4 L0d  5 L1ab  6 STORE(s-1)  7 L1cd
+      // every role walks the same 6 item slots per subtree iteration, each body instantiated once (code size: the kernel
+      // must stay inside the instruction cache):  0 L0ab  1 L2(s-1)  2 L1ab  3 L0cd  4 STORE(s-1)  5 L1cd
+      // (a pair of layer-0 nodes shares one A stage; its join runs before the next pair so that two accumulator slots do)
       for (int s = s_begin; s <= s_end; ++s) {
         const bool cur = s < s_end, prev = s > s_begin;
         if (cur && !(s & 1) && s + 2 < s_end) load_pixels(s / 2 + 1);
 #pragma unroll 1
-        for (int it = 0; it < 8; ++it) {
-          if (it == 6) continue;
-          const int l0 = it < 2 ? it : it - 1;
-          const bool join1 = it == 5 || it == 7;
-          const bool valid = it == 2 ? prev : cur;
-          const int sub = it == 2 ? s - 1 : s;
-          const int off = it == 2 ? off_l2 : (join1 ? off_l1 + (it == 7 ? NCH1 * cb1 : 0) : l0 * cb0);
-          const int n = it == 2 ? NCH2 : (join1 ? NCH1 : 1);
-          const int bytes = it == 2 ? cb2 : (join1 ? cb1 : cb0);
+        for (int it = 0; it < 6; ++it) {
+          if (it == 4) continue;
+          const bool l0 = it == 0 || it == 3, join1 = it == 2 || it == 5;
+          const bool valid = it == 1 ? prev : cur;
+          const int sub = it == 1 ? s - 1 : s;
+          const int off = it == 1 ? off_l2 : (join1 ? off_l1 + (it == 5 ? NCH1 * cb1 : 0) : (it == 3 ? 2 * cb0 : 0));
+          const int n = it == 1 ? NCH2 : (join1 ? NCH1 : 2);
+          const int bytes = it == 1 ? cb2 : (join1 ? cb1 : cb0);
+          (void)l0;
           if (valid) load_chunks(sub, off, n, bytes);
         }
       }
@@ -290,50 +298,61 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
     const bool leader = elect_one();
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0) + uint32_t(g * FR_GCOLS);
     Ring rw(FR_NW), ra(FR_NA);
-    auto mma_item = [&](int nch, int nn, uint32_t dcol, int dslot, bool first_exact) {
+    // One item = nch 32-term chunks, two per A stage.  pair = true (layer 0): every chunk is a node of its own -- fresh
+    // accumulator dcol + 16 h, barrier dslot + h, its weight stage (with the node's head) released with its MMAs.
+    // pair = false (joins): all chunks accumulate into dcol; the first weight stage carries the head the expansion warps
+    // read for every chunk, so it is released last.
+    auto mma_item = [&](int nch, int nn, uint32_t dcol, int dslot, bool pair) {
       const uint32_t idesc = fr_idesc(nn);
       const uint32_t lbo = uint32_t(nn / 8) * 128u, sbo = 128u, lo_off = uint32_t(nn) * 64u;
       const int ws0 = rw.idx;
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c, rw.next(), ra.next()) {
+      for (int c = 0; c < nch; ++c, rw.next()) {
+        const int h = c & 1;
+        const bool last_of_stage = h == 1 || c == nch - 1;
         fr_wait<FR_SLEEP_MMA>(barsu + 8u * uint32_t(FRB_WFULL + rw.idx), rw.par);
-        fr_wait<FR_SLEEP_MMA>(gbu + 8u * uint32_t(FRB_AFULL + ra.idx), ra.par);
+        if (h == 0) fr_wait<FR_SLEEP_MMA>(gbu + 8u * uint32_t(FRB_AFULL + ra.idx), ra.par);
         tc_fence_after();
         if (leader) {
           const uint32_t wbase = smem_u32(wring + size_t(rw.idx) * FR_WSTAGE + FR_HEAD);
-          const uint32_t a_hi = tb + uint32_t(FR_COL_A + 32 * ra.idx), a_lo = a_hi + 16u;
+          const uint32_t a_hi = tb + uint32_t(FR_COL_A + FR_ASTAGE * ra.idx + 16 * h), a_lo = a_hi + uint32_t(FR_ALO);
+          const uint32_t d = tb + dcol + (pair ? 16u * uint32_t(h) : 0u);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const uint64_t bhi = tc_desc(wbase + uint32_t(2 * j) * lbo, lbo, sbo);
             const uint64_t blo = tc_desc(wbase + lo_off + uint32_t(2 * j) * lbo, lbo, sbo);
-            fr_mma(tb + dcol, a_hi + 8u * j, bhi, idesc, (c | j) ? 1u : 0u);
-            fr_mma(tb + dcol, a_hi + 8u * j, blo, idesc, 1u);
-            if (!(first_exact && j == 0)) fr_mma(tb + dcol, a_lo + 8u * j, bhi, idesc, 1u);   // pixels are exact in FP16
+            fr_mma(d, a_hi + 8u * j, bhi, idesc, ((pair ? 0 : c) | j) ? 1u : 0u);
+            fr_mma(d, a_hi + 8u * j, blo, idesc, 1u);
+            if (!(pair && j == 0)) fr_mma(d, a_lo + 8u * j, bhi, idesc, 1u);   // pixels are exact in FP16
           }
-          fr_commit(gbu + 8u * uint32_t(FRB_AFREE + ra.idx));
-          // the first chunk of an item carries the head the expansion warps read for every chunk: it is released last
-          if (c > 0 || nch == 1) fr_commit(barsu + 8u * uint32_t(FRB_WFREE + rw.idx));
-          if (c == nch - 1) {
-            if (nch > 1) fr_commit(barsu + 8u * uint32_t(FRB_WFREE + ws0));
-            fr_commit(gbu + 8u * uint32_t(FRB_DFULL + dslot));
+          if (last_of_stage) fr_commit(gbu + 8u * uint32_t(FRB_AFREE + ra.idx));
+          if (pair) {
+            fr_commit(barsu + 8u * uint32_t(FRB_WFREE + rw.idx));
+            fr_commit(gbu + 8u * uint32_t(FRB_DFULL + dslot + h));
+          } else {
+            if (c > 0 || nch == 1) fr_commit(barsu + 8u * uint32_t(FRB_WFREE + rw.idx));
+            if (c == nch - 1) {
+              if (nch > 1) fr_commit(barsu + 8u * uint32_t(FRB_WFREE + ws0));
+              fr_commit(gbu + 8u * uint32_t(FRB_DFULL + dslot));
+            }
           }
         }
         __syncwarp();
+        if (last_of_stage) ra.next();
       }
     };
     for (int s = s_begin; s <= s_end; ++s) {
       const bool cur = s < s_end, prev = s > s_begin;
 #pragma unroll 1
-      for (int it = 0; it < 8; ++it) {
-        if (it == 6) continue;
-        const int l0 = it < 2 ? it : it - 1;
-        const bool join1 = it == 5 || it == 7;
-        const bool valid = it == 2 ? prev : cur;
-        const int nch = it == 2 ? NCH2 : (join1 ? NCH1 : 1);
-        const int nn = it == 2 ? fd.nn2 : (join1 ? fd.nn1 : fd.nn0);
-        const uint32_t dcol = it == 2 ? FR_COL_L2 : (join1 ? FR_COL_L1 + (it == 7 ? 32 : 0) : FR_COL_L0 + 16 * l0);
-        const int dslot = it == 2 ? 6 : (join1 ? (it == 7 ? 5 : 4) : l0);
-        if (valid) mma_item(nch, nn, dcol, dslot, it != 2 && !join1);
+      for (int it = 0; it < 6; ++it) {
+        if (it == 4) continue;
+        const bool l0 = it == 0 || it == 3, join1 = it == 2 || it == 5;
+        const bool valid = it == 1 ? prev : cur;
+        const int nch = it == 1 ? NCH2 : (join1 ? NCH1 : 2);
+        const int nn = it == 1 ? fd.nn2 : (join1 ? fd.nn1 : fd.nn0);
+        const uint32_t dcol = it == 1 ? FR_COL_L2 : (join1 ? FR_COL_L1 + (it == 5 ? 32 : 0) : FR_COL_L0);
+        const int dslot = it == 1 ? 6 : (join1 ? (it == 5 ? 5 : 4) : (it == 3 ? 2 : 0));
+        if (valid) mma_item(nch, nn, dcol, dslot, l0);
       }
     }
   } else {
@@ -370,7 +389,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
         flush();
         fr_wait(gbu + 8u * uint32_t(FRB_AFREE + ra.idx), ra.par ^ 1u);
         tc_fence_after();
-        return lane_base + uint32_t(FR_COL_A + 32 * ra.idx);
+        return lane_base + uint32_t(FR_COL_A + FR_ASTAGE * ra.idx);
       }
       __device__ __forceinline__ void release() {
         pending = ra.idx;
@@ -381,51 +400,57 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
 
     auto head_of = [&](int stage) { return reinterpret_cast<const float*>(wring + size_t(stage) * FR_WSTAGE); };
 
-    auto item_l0 = [&](int sub, int i) {
+    auto item_l0 = [&](int sub, int pair) {                    // nodes 2 pair, 2 pair + 1 of the subtree: one A stage, one hand-over
       const int q = sub & 1;
-      if (i == 0 && q == 0) fr_wait(gbu + 8u * uint32_t(FRB_XFULL + rx.idx), rx.par);
+      if (pair == 0 && q == 0) fr_wait(gbu + 8u * uint32_t(FRB_XFULL + rx.idx), rx.par);
       const uint8_t* box = xring + size_t(g * FR_NX + rx.idx) * FR_XSTAGE;
-      const int off = __ldg(fd.l0_off + sub * 4 + i);
-      const int dy = off & 0xff, dx = off >> 8;
-      float px[8];                                             // rows 2 half, 2 half + 1 of the node's 4 x 4 pixels
-      if (IN_MODE == FR_IN_ROWMAJOR) {
-        // box = [8 rows][128 windows][16 bytes] (tensor dimensions ordered x, window, y): consecutive lanes read words
-        // 16 bytes apart -- 4 wavefronts per load, as many as the byte loads of the window-minor form need
-        const uint8_t* wrow = box + win * 16 + dx;
+      uint32_t stage = 0;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int off = __ldg(fd.l0_off + sub * 4 + 2 * pair + h);
+        const int dy = off & 0xff, dx = off >> 8;
+        float px[8];                                           // rows 2 half, 2 half + 1 of the node's 4 x 4 pixels
+        if (IN_MODE == FR_IN_ROWMAJOR) {
+          // box = [8 rows][128 windows][16 bytes] (tensor dimensions ordered x, window, y): consecutive lanes read words
+          // 16 bytes apart -- 4 wavefronts per load, as many as the byte loads of the window-minor form need
+          const uint8_t* wrow = box + win * 16 + dx;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const uint32_t u = *reinterpret_cast<const uint32_t*>(wrow + (dy + 2 * half + r) * (16 * TILE));
-          const float4 f = u8x4_to_float4(u);
-          px[4 * r + 0] = f.x; px[4 * r + 1] = f.y; px[4 * r + 2] = f.z; px[4 * r + 3] = f.w;
+          for (int r = 0; r < 2; ++r) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(wrow + (dy + 2 * half + r) * (16 * TILE));
+            const float4 f = u8x4_to_float4(u);
+            px[4 * r + 0] = f.x; px[4 * r + 1] = f.y; px[4 * r + 2] = f.z; px[4 * r + 3] = f.w;
+          }
+        } else {
+          // box = [8 rows][16 pixels][128 windows]
+          const uint8_t* col = box + ((dy + 2 * half) * 16 + dx) * TILE + win;
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+              px[4 * r + x] = __uint_as_float(0x4B000000u | uint32_t(col[(r * 16 + x) * TILE])) - 8388608.0f;
         }
-      } else {
-        // box = [8 rows][16 pixels][128 windows]
-        const uint8_t* col = box + ((dy + 2 * half) * 16 + dx) * TILE + win;
+        fr_wait(barsu + 8u * uint32_t(FRB_WFULL + rw.idx), rw.par);
+        const float* mean = head_of(rw.idx) + 8 * half;
+        rw.next();
+        uint32_t hi_id[4], hi_pw[4], lo_pw[4];
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-            px[4 * r + x] = __uint_as_float(0x4B000000u | uint32_t(col[(r * 16 + x) * TILE])) - 8388608.0f;
+        for (int k = 0; k < 8; k += 4) {
+          const float4 m = *reinterpret_cast<const float4*>(mean + k);
+          hi_id[k / 2] = fr_pack(px[k], px[k + 1]);            // identity terms: 8-bit integers, exact in FP16
+          hi_id[k / 2 + 1] = fr_pack(px[k + 2], px[k + 3]);
+          fr_split(abspow(px[k] - m.x, fd.p0), abspow(px[k + 1] - m.y, fd.p0), hi_pw[k / 2], lo_pw[k / 2]);
+          fr_split(abspow(px[k + 2] - m.z, fd.p0), abspow(px[k + 3] - m.w, fd.p0), hi_pw[k / 2 + 1], lo_pw[k / 2 + 1]);
+        }
+        // the node's chunk of the stage: hi columns 16 h + 0-7 identity (K step 0), + 8-15 power (K step 1); lo pieces
+        // FR_ALO columns further (the identity's are zero and never read)
+        if (h == 0) stage = pub.acquire();
+        const uint32_t col = stage + uint32_t(16 * h + 4 * half);
+        tmem_st4(col, hi_id);
+        tmem_st4(col + 8, hi_pw);
+        tmem_st4(col + FR_ALO + 8, lo_pw);
       }
-      fr_wait(barsu + 8u * uint32_t(FRB_WFULL + rw.idx), rw.par);
-      const float* mean = head_of(rw.idx) + 8 * half;
-      rw.next();
-      uint32_t hi_id[4], hi_pw[4], lo_pw[4];
-#pragma unroll
-      for (int k = 0; k < 8; k += 4) {
-        const float4 m = *reinterpret_cast<const float4*>(mean + k);
-        hi_id[k / 2] = fr_pack(px[k], px[k + 1]);              // identity terms: 8-bit integers, exact in FP16
-        hi_id[k / 2 + 1] = fr_pack(px[k + 2], px[k + 3]);
-        fr_split(abspow(px[k] - m.x, fd.p0), abspow(px[k + 1] - m.y, fd.p0), hi_pw[k / 2], lo_pw[k / 2]);
-        fr_split(abspow(px[k + 2] - m.z, fd.p0), abspow(px[k + 3] - m.w, fd.p0), hi_pw[k / 2 + 1], lo_pw[k / 2 + 1]);
-      }
-      // A stage of the node: hi columns 0-7 identity (K step 0), 8-15 power (K step 1); lo columns 16 + the same
-      const uint32_t col = pub.acquire() + uint32_t(4 * half);
-      tmem_st4(col, hi_id);
-      tmem_st4(col + 8, hi_pw);
-      tmem_st4(col + 24, lo_pw);
       pub.release();
-      if (i == 3 && q == 1) {                                  // pixel box of the pair consumed
+      if (pair == 1 && q == 1) {                               // pixel box of the pair of subtrees consumed
         __syncwarp();
         if (lane == 0) fr_arrive(gbu + 8u * uint32_t(FRB_XFREE + rx.idx));
         rx.next();
@@ -438,7 +463,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
       fr_wait(barsu + 8u * uint32_t(FRB_WFULL + rw.idx), rw.par);
       const float* head = head_of(rw.idx);
       rw.advance(NCH1);
-      FrJoin<NP1>::run(lane_base + FR_COL_L0 + 32 * h + 16 * half, head + NP1 * half, head + 2 * NP1 + NP1 * half, half, fd.s0,
+      FrJoin<NP1>::run(lane_base + FR_COL_L0 + 16 * half, head + NP1 * half, head + 2 * NP1 + NP1 * half, half, fd.s0,
                        fd.clo0, fd.chi0, fd.p1, pub);
     };
     auto item_l2 = [&](uint32_t par) {
@@ -484,14 +509,14 @@ __global__ void __launch_bounds__(FR_THREADS, 1)
       const bool cur = s < s_end, prev = s > s_begin;
       const uint32_t par = uint32_t(s - s_begin) & 1u, ppar = par ^ 1u;
 #pragma unroll 1
-      for (int it = 0; it < 8; ++it) {
-        if (it == 2) {
+      for (int it = 0; it < 6; ++it) {
+        if (it == 1) {
           if (prev) item_l2(ppar);
-        } else if (it == 6) {
+        } else if (it == 4) {
           if (prev) item_store(s - 1, ppar);
         } else if (cur) {
-          if (it == 5 || it == 7) item_l1(it == 7 ? 1 : 0, par);
-          else item_l0(s, it < 2 ? it : it - 1);
+          if (it == 2 || it == 5) item_l1(it == 5 ? 1 : 0, par);
+          else item_l0(s, it == 3 ? 1 : 0);
         }
       }
     }
