@@ -516,7 +516,7 @@ extern "C" int hgsfa_plan_create(const void* blob, size_t nbytes, int device, hg
               // all products x_i x_j, r0 <= i <= j < r0 + n in row-major order (QT expansion)?  -> register-resident form
               const int len = sgm.k1 - sgm.k0, r0 = terms[sgm.k0].i;
               int n = 0;
-              for (int c = 3; c <= 16; ++c) if (c * (c + 1) / 2 == len) n = c;
+              for (int c = 3; c <= 16; ++c) if (c * (c + 1) / 2 == len && tc_tri_size(c)) n = c;
               bool tri = n > 0;
               for (int q = 0; tri && q < len; ++q)
                 tri = terms[sgm.k0 + q].i == r0 + tri_row(n, q) && terms[sgm.k0 + q].j == r0 + tri_col(n, q);

@@ -332,6 +332,7 @@ __device__ __forceinline__ void tc_seg_rows(const IN_T* xp, const float* mp, int
 // The N operands are loaded once into registers; the enumeration is unrolled at compile time, so a term
 // costs one FMUL plus the TF32 split.  A piece covers the 8-term groups [t0 / 8, (t0 + cnt + 7) / 8).
 constexpr int OP_TRI = 9;            // segment-only op code: p = N, ibase = r0, nomean = t0
+__host__ __device__ constexpr bool tc_tri_size(int n) { return n == 10; }   // cuicuilco's s10 selectors (the shipped thin networks)
 __host__ __device__ constexpr int tri_row(int n, int idx) {
   int i = 0, len = n;
   while (idx >= len && len > 0) { idx -= len; --len; ++i; }
@@ -623,8 +624,10 @@ __global__ void __launch_bounds__(TC_THREADS, HGSFA_TC_MINB)
               const float* mr = mean + sg.ibase;
               switch (int(sg.p)) {
 #define HG_TRI(N_) case N_: tc_seg_tri<IN_T, N_, F16>(xr, mr, sg.nomean, cnt, col, op.prod_scale); break;
-                HG_TRI(3) HG_TRI(4) HG_TRI(5) HG_TRI(6) HG_TRI(7) HG_TRI(8) HG_TRI(9) HG_TRI(10) HG_TRI(11) HG_TRI(12)
-                HG_TRI(13) HG_TRI(14) HG_TRI(15) HG_TRI(16)
+                // register-resident form for the sizes in TC_TRI_SIZES only: every instantiation is 0.6-1.5 k instructions, and
+                // with all of N = 3..16 the kernel was 148 KB of SASS -- past the instruction cache, 4 % slower on every
+                // layer (profiles/README_r02.md item 17); other sizes stay table-driven products (OP_MUL below)
+                HG_TRI(10)
 #undef HG_TRI
                 default: break;
               }
